@@ -1,0 +1,175 @@
+"""ctypes binding of lib/libfft_b200.so - the B200 drop-in for the reference's FFT hot path.
+
+The product is the shared library (C99 host API + sm_100a kernels); this module only loads it and
+mirrors the reference's public C API (include/fft_auto.h, include/fft_gpu.h) one to one, so tests and
+bench.py call exactly what a C program linked against the library would call. There is no Python or
+CPU implementation behind these names: if the library is missing, import fails.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libfft_b200.so")
+
+FFT_FORWARD, FFT_INVERSE = -1, 1
+FFT_GPU_CUDA, FFT_GPU_AUTO = 1, -1
+FFT_ESTIMATE, FFT_PREFER_GPU = 0, 1 << 9
+FFTB200_C2C, FFTB200_BLUESTEIN, FFTB200_R2C = 0, 1, 2
+
+_vp, _dp = C.c_void_p, C.POINTER(C.c_double)
+
+if not os.path.exists(LIB_PATH):
+    raise ImportError("libfft_b200.so is not built: run `python fft-implementation-in-c_b200/build.py` "
+                      "(there is no fallback implementation)")
+lib = C.CDLL(LIB_PATH)
+
+_SIGS = {
+    # include/fft_gpu.h
+    "fft_gpu_init": (C.c_int, [C.c_int]),
+    "fft_gpu_cleanup": (None, []),
+    "fft_gpu_available": (C.c_int, []),
+    "fft_gpu_get_backend": (C.c_int, []),
+    "fft_gpu_alloc": (_vp, [C.c_size_t]),
+    "fft_gpu_free": (None, [_vp]),
+    "fft_gpu_copy_h2d": (None, [_vp, _vp, C.c_size_t]),
+    "fft_gpu_copy_d2h": (None, [_vp, _vp, C.c_size_t]),
+    "fft_gpu_plan_1d": (_vp, [C.c_int, C.c_int, C.c_int]),
+    "fft_gpu_execute": (None, [_vp, _vp, _vp]),
+    "fft_gpu_destroy_plan": (None, [_vp]),
+    "fft_gpu_dft_1d": (C.c_int, [_vp, _vp, C.c_int, C.c_int]),
+    "fft_gpu_dft_1d_batch": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int]),
+    "fft_gpu_plan_2d": (_vp, [C.c_int, C.c_int, C.c_int]),
+    "fft_gpu_dft_2d": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int]),
+    "fft_gpu_get_device_name": (C.c_char_p, []),
+    "fft_gpu_get_memory_info": (None, [C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]),
+    "fft_gpu_set_device": (C.c_int, [C.c_int]),
+    # include/fft_auto.h
+    "fft_plan_dft_1d": (_vp, [C.c_int, _vp, _vp, C.c_int, C.c_uint]),
+    "fft_execute": (None, [_vp]),
+    "fft_execute_dft": (None, [_vp, _vp, _vp]),
+    "fft_destroy_plan": (None, [_vp]),
+    "fft_auto": (C.c_int, [_vp, _vp, C.c_int, C.c_int]),
+    "fft_plan_r2c_1d": (_vp, [C.c_int, _vp, _vp, C.c_uint]),
+    "fft_plan_c2r_1d": (_vp, [C.c_int, _vp, _vp, C.c_uint]),
+    "fft_plan_dft_2d": (_vp, [C.c_int, C.c_int, _vp, _vp, C.c_int, C.c_uint]),
+    "fft_export_wisdom_to_string": (_vp, []),
+    "fft_import_wisdom_from_string": (C.c_int, [C.c_char_p]),
+    "fft_get_hardware_capabilities": (C.c_uint, []),
+    "fft_plan_with_nthreads": (None, [C.c_int]),
+    "fft_alloc_complex": (_vp, [C.c_size_t]),
+    "fft_alloc_real": (_vp, [C.c_size_t]),
+    "fft_free": (None, [_vp]),
+    "fft_version": (C.c_char_p, []),
+    # include/fftb200.h (engine C-ABI)
+    "fftb200_device_count": (C.c_int, []),
+    "fftb200_set_device": (C.c_int, [C.c_int]),
+    "fftb200_get_device": (C.c_int, []),
+    "fftb200_device_name": (C.c_char_p, []),
+    "fftb200_mem_info": (C.c_int, [C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]),
+    "fftb200_sm_count": (C.c_int, []),
+    "fftb200_device_reset": (C.c_int, []),
+    "fftb200_malloc": (_vp, [C.c_size_t]),
+    "fftb200_free": (None, [_vp]),
+    "fftb200_host_alloc": (_vp, [C.c_size_t]),
+    "fftb200_host_free": (None, [_vp]),
+    "fftb200_memcpy_h2d": (C.c_int, [_vp, _vp, C.c_size_t]),
+    "fftb200_memcpy_d2h": (C.c_int, [_vp, _vp, C.c_size_t]),
+    "fftb200_memcpy_d2d": (C.c_int, [_vp, _vp, C.c_size_t]),
+    "fftb200_memset": (C.c_int, [_vp, C.c_int, C.c_size_t]),
+    "fftb200_fill_splitmix": (C.c_int, [_vp, C.c_ulonglong, C.c_ulonglong, C.c_ulonglong]),
+    "fftb200_plan_create": (C.c_int, [C.POINTER(_vp), _vp]),
+    "fftb200_plan_exec": (C.c_int, [_vp, _vp, _vp]),
+    "fftb200_plan_exec_async": (C.c_int, [_vp, _vp, _vp]),
+    "fftb200_plan_sync": (C.c_int, [_vp]),
+    "fftb200_plan_exec_host": (C.c_int, [_vp, _vp, _vp]),
+    "fftb200_plan_destroy": (None, [_vp]),
+    "fftb200_plan_launches": (C.c_int, [_vp]),
+    "fftb200_plan_describe": (C.c_char_p, [_vp]),
+    "fftb200_timer_start": (C.c_int, [_vp]),
+    "fftb200_timer_stop": (C.c_int, [_vp, C.POINTER(C.c_float)]),
+    "fftb200_pointwise_mul": (C.c_int, [_vp, _vp, _vp, C.c_size_t]),
+    "fftb200_last_error": (C.c_char_p, []),
+    # host-library helpers (not part of the reference API)
+    "fftb200_engine_of": (_vp, [_vp]),
+    "fftb200_devptr_of": (_vp, [_vp]),
+    "fftb200_host_twiddles": (_vp, [C.c_int]),
+    "fftb200_host_chirp": (None, [_vp, C.c_int, C.c_int]),
+}
+EXPORTS = sorted(_SIGS)
+for _name, (_res, _args) in _SIGS.items():
+    _f = getattr(lib, _name)  # AttributeError here = the library does not export a declared symbol
+    _f.restype, _f.argtypes = _res, _args
+
+
+def ptr(a):
+    """Address of a contiguous numpy array as void*."""
+    assert a.flags["C_CONTIGUOUS"]
+    return a.ctypes.data
+
+
+def require_gpu():
+    if lib.fft_gpu_available() != 1:
+        raise RuntimeError("no CUDA device: the B200 FFT path has no CPU fallback")
+    if lib.fft_gpu_init(FFT_GPU_AUTO) != 0:
+        raise RuntimeError("fft_gpu_init failed: " + lib.fftb200_last_error().decode())
+
+
+def fft_auto(x, sign=-1):
+    """fft_auto(in, out, n, sign) on a 1-D complex128 array; returns the output array."""
+    x = np.ascontiguousarray(x, dtype=np.complex128)
+    out = np.empty_like(x)
+    if lib.fft_auto(ptr(x), ptr(out), x.size, sign) != 0:
+        raise RuntimeError("fft_auto failed: " + lib.fftb200_last_error().decode())
+    return out
+
+
+def gpu_fft_batch(x, direction=FFT_FORWARD, inplace=False):
+    """fft_gpu_alloc / copy_h2d / plan_1d(n, batch) / execute / copy_d2h on a 2-D complex128 array."""
+    x = np.ascontiguousarray(x, dtype=np.complex128)
+    batch, n = x.shape
+    require_gpu()
+    m_in = lib.fft_gpu_alloc(x.size)
+    m_out = m_in if inplace else lib.fft_gpu_alloc(x.size)
+    plan = lib.fft_gpu_plan_1d(n, batch, direction)
+    if not m_in or not m_out or not plan:
+        raise RuntimeError("fft_gpu setup failed: " + lib.fftb200_last_error().decode())
+    try:
+        lib.fft_gpu_copy_h2d(m_in, ptr(x), x.size)
+        lib.fft_gpu_execute(plan, m_in, m_out)
+        out = np.empty_like(x)
+        lib.fft_gpu_copy_d2h(ptr(out), m_out, x.size)
+    finally:
+        lib.fft_gpu_destroy_plan(plan)
+        lib.fft_gpu_free(m_in)
+        if not inplace:
+            lib.fft_gpu_free(m_out)
+    return out
+
+
+def r2c(x):
+    """fft_plan_r2c_1d + fft_execute on a 1-D float64 array; returns n/2+1 bins."""
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    out = np.empty(x.size // 2 + 1, dtype=np.complex128)
+    plan = lib.fft_plan_r2c_1d(x.size, ptr(x), ptr(out), 0)
+    if not plan:
+        raise RuntimeError("fft_plan_r2c_1d failed: " + lib.fftb200_last_error().decode())
+    lib.fft_execute(plan)
+    lib.fft_destroy_plan(plan)
+    return out
+
+
+def host_twiddles(n):
+    """The host-built forward stage tables for power-of-two n (n-1 complex), as a numpy copy."""
+    p = lib.fftb200_host_twiddles(n)
+    if not p:
+        raise RuntimeError("fftb200_host_twiddles failed")
+    buf = (C.c_double * (2 * (n - 1))).from_address(p)
+    return np.frombuffer(buf, dtype=np.complex128).copy()
+
+
+def host_chirp(n, direction=-1):
+    c = np.empty(n, dtype=np.complex128)
+    lib.fftb200_host_chirp(ptr(c), n, direction)
+    return c

@@ -1,0 +1,71 @@
+"""In-tree build of lib/libfft_b200.so: sm_100a CUDA kernels + C-ABI (csrc/) and the C99 host library
+that carries the reference's public API (host/). Usage: python build.py [--force] [--verbose]."""
+import os
+import subprocess
+import sys
+from concurrent.futures import ThreadPoolExecutor
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+OBJ = os.path.join(HERE, "build")
+LIB = os.path.join(HERE, "lib", "libfft_b200.so")
+
+NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+GCC = "/usr/bin/gcc"
+NVCC_FLAGS = ["-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3",
+              "-Xcompiler", "-fPIC", "-ccbin", "/usr/bin/g++"]
+# The host tables replicate the reference's rounding sequence explicitly (host/ref_twiddle.c): no
+# fast-math, no implicit FMA contraction. x86-64-v3 = AVX2+FMA so fma() is one instruction.
+HOST_FLAGS = ["-O2", "-std=c99", "-march=x86-64-v3", "-ffp-contract=off", "-fPIC", "-Wall", "-Wextra",
+              "-I" + os.path.join(ROOT, "include")]
+
+
+def _newer(src_list, target):
+    if not os.path.exists(target):
+        return True
+    t = os.path.getmtime(target)
+    return any(os.path.getmtime(s) > t for s in src_list)
+
+
+def build(force=False, verbose=False):
+    os.makedirs(OBJ, exist_ok=True)
+    os.makedirs(os.path.dirname(LIB), exist_ok=True)
+    csrc = os.path.join(HERE, "csrc")
+    host = os.path.join(HERE, "host")
+    headers = [os.path.join(csrc, f) for f in os.listdir(csrc) if f.endswith((".cuh", ".h"))]
+    headers += [os.path.join(ROOT, "include", f) for f in os.listdir(os.path.join(ROOT, "include"))]
+    headers += [os.path.join(host, f) for f in os.listdir(host) if f.endswith(".h")]
+    headers.append(os.path.abspath(__file__))
+    jobs = []
+    objs = []
+    for f in sorted(os.listdir(csrc)):
+        if f.endswith(".cu"):
+            o = os.path.join(OBJ, f[:-3] + ".o")
+            objs.append(o)
+            if force or _newer([os.path.join(csrc, f)] + headers, o):
+                jobs.append([NVCC] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) +
+                            ["-c", os.path.join(csrc, f), "-o", o])
+    for f in sorted(os.listdir(host)):
+        if f.endswith(".c"):
+            o = os.path.join(OBJ, f[:-2] + ".o")
+            objs.append(o)
+            if force or _newer([os.path.join(host, f)] + headers, o):
+                jobs.append([GCC] + HOST_FLAGS + ["-c", os.path.join(host, f), "-o", o])
+
+    def run(cmd):
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0 or verbose:
+            sys.stderr.write(" ".join(cmd) + "\n" + r.stdout + r.stderr)
+        if r.returncode != 0:
+            raise RuntimeError("build failed: " + " ".join(cmd))
+
+    with ThreadPoolExecutor(max_workers=min(8, max(1, len(jobs)))) as ex:
+        list(ex.map(run, jobs))
+    if jobs or not os.path.exists(LIB):
+        run([NVCC, "-shared", "-o", LIB] + objs + ["-Xcompiler", "-fPIC", "-ccbin", "/usr/bin/g++",
+                                                    "-lpthread", "-lm", "-cudart", "static"])
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))

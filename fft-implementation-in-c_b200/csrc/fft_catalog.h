@@ -1,0 +1,34 @@
+// fft_catalog.h - table of compiled tile-kernel variants shared between the kernel TUs and the planner.
+#pragma once
+#include "fft_tile.cuh"
+
+namespace fftb200 {
+
+struct KernelInfo {
+    int mode, logp, logc, triv, nt, threads;
+    size_t smem;
+    const void* func;
+    void (*launch)(const TileArgs&, int grid, cudaStream_t);
+};
+
+template <class C>
+static void launch_tile(const TileArgs& a, int grid, cudaStream_t s) {
+    fft_tile_kernel<C><<<grid, C::THREADS, C::SMEM_BYTES, s>>>(a);
+}
+
+template <class C>
+static KernelInfo make_info() {
+    KernelInfo k;
+    k.mode = C::MODE; k.logp = C::LOGP; k.logc = C::LOGC; k.triv = C::TRIV ? 1 : 0; k.nt = C::NT;
+    k.threads = C::THREADS; k.smem = C::SMEM_BYTES;
+    k.func = (const void*)fft_tile_kernel<C>;
+    k.launch = launch_tile<C>;
+    return k;
+}
+
+// each returns a static array; defined in fft_kernels_{contig,strided,last}.cu
+const KernelInfo* kernels_contig(int* count);
+const KernelInfo* kernels_strided(int* count);
+const KernelInfo* kernels_last(int* count);
+
+}  // namespace fftb200

@@ -1,0 +1,14 @@
+// Last-pass variants of multi-pass plans: contiguous P-point columns in, natural-order rows out.
+#include "fft_catalog.h"
+namespace fftb200 {
+typedef TileCfg<6, 4, 4, 1, MODE_LAST, false, 3, 3, 0, 0, 8, 4> L6;
+typedef TileCfg<7, 4, 4, 1, MODE_LAST, false, 3, 4, 0, 0, 4, 4> L7;
+typedef TileCfg<8, 4, 4, 1, MODE_LAST, false, 4, 4, 0, 0, 2, 4> L8;
+typedef TileCfg<9, 3, 4, 1, MODE_LAST, false, 3, 3, 3, 0, 2, 3> L9;
+
+const KernelInfo* kernels_last(int* count) {
+    static KernelInfo tab[] = {make_info<L6>(), make_info<L7>(), make_info<L8>(), make_info<L9>()};
+    *count = (int)(sizeof(tab) / sizeof(tab[0]));
+    return tab;
+}
+}  // namespace fftb200

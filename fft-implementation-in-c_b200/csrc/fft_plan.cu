@@ -1,0 +1,480 @@
+// fft_plan.cu - C-ABI of the engine (include/fftb200.h): device lifecycle, memory, plan construction
+// (which tile-kernel variants run, in which order, through which buffers) and execution.
+//
+// Replaces gpu/fft_cuda.cu of the reference (cuFFT wrapper, never built): plan = cufftPlanMany
+// (:138-163), exec = cufftExecZ2Z + device sync (:166-185), alloc/copies (:103-135).
+// There is no CPU fallback anywhere in this file: without a CUDA device every call fails.
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/fftb200.h"
+#include "fft_aux.cuh"
+#include "fft_catalog.h"
+
+using namespace fftb200;
+
+// ---------------------------------------------------------------------------------------------
+// errors
+// ---------------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+
+static int fail(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    if (getenv("FFTB200_VERBOSE")) fprintf(stderr, "fftb200: %s\n", g_err);
+    return -1;
+}
+#define CU(call)                                                                           \
+    do {                                                                                   \
+        cudaError_t e_ = (call);                                                           \
+        if (e_ != cudaSuccess) return fail("%s: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+extern "C" const char* fftb200_last_error(void) { return g_err; }
+
+// ---------------------------------------------------------------------------------------------
+// per-device state
+// ---------------------------------------------------------------------------------------------
+struct DeviceState {
+    bool init = false;
+    int sms = 0;
+    cd* tab = nullptr;   // largest twiddle table uploaded so far (older, smaller ones stay alive in `old`)
+    int tab_n = 0;
+    std::vector<cd*> old;
+    char name[256] = "";
+};
+static DeviceState g_dev[64];
+static std::mutex g_mu;
+
+static int cur_device(DeviceState** ds) {
+    int d = 0;
+    CU(cudaGetDevice(&d));
+    if (d < 0 || d >= 64) return fail("device index %d out of range", d);
+    DeviceState& s = g_dev[d];
+    if (!s.init) {
+        cudaDeviceProp p;
+        CU(cudaGetDeviceProperties(&p, d));
+        s.sms = p.multiProcessorCount;
+        snprintf(s.name, sizeof(s.name), "%s", p.name);
+        s.init = true;
+    }
+    *ds = &s;
+    return 0;
+}
+
+extern "C" int fftb200_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+extern "C" int fftb200_set_device(int device) { CU(cudaSetDevice(device)); return 0; }
+extern "C" int fftb200_get_device(void) { int d = -1; if (cudaGetDevice(&d) != cudaSuccess) return -1; return d; }
+extern "C" const char* fftb200_device_name(void) {
+    DeviceState* s;
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (cur_device(&s) != 0) return "";
+    return s->name;
+}
+extern "C" int fftb200_sm_count(void) {
+    DeviceState* s;
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (cur_device(&s) != 0) return -1;
+    return s->sms;
+}
+extern "C" int fftb200_mem_info(size_t* free_bytes, size_t* total_bytes) {
+    size_t f = 0, t = 0;
+    CU(cudaMemGetInfo(&f, &t));
+    if (free_bytes) *free_bytes = f;
+    if (total_bytes) *total_bytes = t;
+    return 0;
+}
+extern "C" int fftb200_device_reset(void) {
+    DeviceState* s;
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (cur_device(&s) != 0) return -1;
+    CU(cudaDeviceSynchronize());
+    if (s->tab) cudaFree(s->tab);
+    for (cd* p : s->old) cudaFree(p);
+    s->old.clear();
+    s->tab = nullptr;
+    s->tab_n = 0;
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// memory
+// ---------------------------------------------------------------------------------------------
+extern "C" void* fftb200_malloc(size_t bytes) {
+    void* p = nullptr;
+    if (bytes == 0) bytes = 16;
+    cudaError_t e = cudaMalloc(&p, bytes);
+    if (e != cudaSuccess) { fail("cudaMalloc(%zu): %s", bytes, cudaGetErrorString(e)); cudaGetLastError(); return nullptr; }
+    return p;
+}
+extern "C" void fftb200_free(void* p) { if (p) cudaFree(p); }
+extern "C" void* fftb200_host_alloc(size_t bytes) {
+    void* p = nullptr;
+    if (bytes == 0) bytes = 16;
+    cudaError_t e = cudaMallocHost(&p, bytes);
+    if (e != cudaSuccess) { fail("cudaMallocHost(%zu): %s", bytes, cudaGetErrorString(e)); cudaGetLastError(); return nullptr; }
+    return p;
+}
+extern "C" void fftb200_host_free(void* p) { if (p) cudaFreeHost(p); }
+// cudaMemcpy from pageable host memory may return while the DMA out of the driver's staging buffer is
+// still in flight on the legacy stream; plan streams are non-blocking, so wait for it explicitly.
+extern "C" int fftb200_memcpy_h2d(void* d, const void* s, size_t n) {
+    CU(cudaMemcpy(d, s, n, cudaMemcpyHostToDevice));
+    CU(cudaStreamSynchronize(cudaStreamLegacy));
+    return 0;
+}
+extern "C" int fftb200_memcpy_d2h(void* d, const void* s, size_t n) { CU(cudaMemcpy(d, s, n, cudaMemcpyDeviceToHost)); return 0; }
+extern "C" int fftb200_memcpy_d2d(void* d, const void* s, size_t n) { CU(cudaMemcpy(d, s, n, cudaMemcpyDeviceToDevice)); CU(cudaStreamSynchronize(cudaStreamLegacy)); return 0; }
+extern "C" int fftb200_memset(void* d, int v, size_t n) { CU(cudaMemset(d, v, n)); CU(cudaStreamSynchronize(cudaStreamLegacy)); return 0; }
+
+extern "C" int fftb200_fill_splitmix(void* dst, unsigned long long seed, unsigned long long first,
+                                     unsigned long long count) {
+    if (!dst) return fail("fill: null pointer");
+    if (count == 0) return 0;
+    fill_splitmix_kernel<<<(unsigned)((count + 255) / 256 > 1u << 20 ? 1u << 20 : (count + 255) / 256), 256>>>(
+        (cd*)dst, seed, first, count);
+    CU(cudaGetLastError());
+    CU(cudaDeviceSynchronize());
+    return 0;
+}
+
+extern "C" int fftb200_pointwise_mul(void* y, const void* a, const void* b, size_t count) {
+    if (!y || !a || !b) return fail("pointwise_mul: null pointer");
+    if (count == 0) return 0;
+    size_t blocks = (count + 255) / 256;
+    if (blocks > (1u << 20)) blocks = 1u << 20;
+    pointwise_mul_kernel<<<(unsigned)blocks, 256>>>((cd*)y, (const cd*)a, (const cd*)b, count, count);
+    CU(cudaGetLastError());
+    CU(cudaDeviceSynchronize());
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// plans
+// ---------------------------------------------------------------------------------------------
+enum { BUF_IN = 0, BUF_OUT = 1, BUF_SCRATCH = 2 };
+
+struct Pass {
+    const KernelInfo* k;
+    int log_m;
+    long long ntiles;
+    int src, dst;
+    int final_pass;
+    int grid;
+};
+
+struct fftb200_plan {
+    int device = 0;
+    int n = 0, batch = 0, dir = -1, kind = FFTB200_C2C;
+    int log_n = 0;             // of the power-of-two transform actually run (n, or Bluestein's m)
+    int m = 0;                 // power-of-two length (== n for C2C / R2C)
+    std::vector<Pass> passes;  // forward or inverse c2c of length m over `batch`
+    const cd* tab = nullptr;
+    cd* scratch = nullptr;     // ping-pong buffer for multi-pass plans
+    cd* work = nullptr;        // Bluestein / R2C: padded complex work array, m * batch
+    cd* chirp = nullptr;       // Bluestein: n entries
+    cd* fb = nullptr;          // Bluestein: FFT_m of the wrapped chirp
+    // host staging (exec_host)
+    cd* d_stage_in = nullptr;
+    cd* d_stage_out = nullptr;
+    cudaStream_t stream = nullptr, stream2 = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    int launches = 0;
+    std::string desc;
+};
+
+static const KernelInfo* find_kernel(int mode, int logp, int triv) {
+    int cnt = 0;
+    const KernelInfo* t = mode == MODE_CONTIG ? kernels_contig(&cnt) : mode == MODE_STRIDED ? kernels_strided(&cnt) : kernels_last(&cnt);
+    for (int i = 0; i < cnt; i++)
+        if (t[i].logp == logp && t[i].triv == triv) return &t[i];
+    return nullptr;
+}
+
+static int ilog2(long long n) { int l = 0; while (n > 1) { n >>= 1; l++; } return l; }
+
+// Split log2 N into per-pass sizes (each 6..9 bits, larger first); <= 13 bits is a single CONTIG pass.
+static std::vector<int> split_passes(int log_n) {
+    std::vector<int> v;
+    if (log_n <= 13) { v.push_back(log_n); return v; }
+    const char* force = getenv("FFTB200_SPLIT");  // e.g. "8,8" for tuning
+    if (force) {
+        int sum = 0;
+        std::vector<int> f;
+        for (const char* p = force; *p;) {
+            int x = (int)strtol(p, (char**)&p, 10);
+            if (x > 0) { f.push_back(x); sum += x; }
+            if (*p == ',') p++;
+        }
+        if (sum == log_n) return f;
+    }
+    int np = (log_n + 8) / 9;
+    if (np < 2) np = 2;
+    int base = log_n / np, extra = log_n % np;
+    for (int i = 0; i < np; i++) v.push_back(base + (i < extra ? 1 : 0));
+    return v;
+}
+
+static int build_passes(fftb200_plan* p, DeviceState* ds) {
+    const int L = p->log_n;
+    std::vector<int> sizes = split_passes(L);
+    const int np = (int)sizes.size();
+    int log_m = 0;
+    const int persistent = getenv("FFTB200_PERSISTENT") ? atoi(getenv("FFTB200_PERSISTENT")) : 1;
+    for (int i = 0; i < np; i++) {
+        Pass ps;
+        const int lp = sizes[i];
+        int mode;
+        if (np == 1) mode = MODE_CONTIG;
+        else if (i == np - 1) mode = MODE_LAST;
+        else mode = MODE_STRIDED;
+        ps.k = find_kernel(mode, lp, mode == MODE_CONTIG ? 1 : (mode == MODE_STRIDED ? (i == 0) : 0));
+        if (!ps.k) return fail("no kernel variant for mode %d, 2^%d points", mode, lp);
+        ps.log_m = log_m;
+        if (mode == MODE_CONTIG) {
+            ps.ntiles = ((long long)p->batch + ps.k->nt - 1) / ps.k->nt;
+        } else if (mode == MODE_STRIDED) {
+            const int log_rest = L - log_m - lp;
+            if (log_rest < ps.k->logc) return fail("pass split leaves too few columns");
+            ps.ntiles = (long long)p->batch << (log_rest - ps.k->logc + log_m);
+        } else {
+            if (log_m < ps.k->logc) return fail("last pass too wide");
+            ps.ntiles = (long long)p->batch << (log_m - ps.k->logc);
+        }
+        // ping-pong so that the final pass lands in OUT; the first pass always reads IN
+        ps.src = (i == 0) ? BUF_IN : (((np - 1 - (i - 1)) % 2 == 0) ? BUF_OUT : BUF_SCRATCH);
+        ps.dst = ((np - 1 - i) % 2 == 0) ? BUF_OUT : BUF_SCRATCH;
+        ps.final_pass = (i == np - 1);
+        CU(cudaFuncSetAttribute(ps.k->func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ps.k->smem));
+        int occ = 0;
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ps.k->func, ps.k->threads, ps.k->smem));
+        if (occ < 1) return fail("kernel variant does not fit on an SM");
+        long long g = persistent ? (long long)ds->sms * occ : ps.ntiles;
+        if (g > ps.ntiles) g = ps.ntiles;
+        if (g > 0x7fffffffLL) g = 0x7fffffffLL;
+        if (g < 1) g = 1;
+        ps.grid = (int)g;
+        p->passes.push_back(ps);
+        char b[64];
+        snprintf(b, sizeof(b), "%s%c%d(occ%d)", i ? "+" : "", mode == MODE_CONTIG ? 'C' : mode == MODE_STRIDED ? (i == 0 ? 'F' : 'M') : 'L', lp, occ);
+        p->desc += b;
+        log_m += lp;
+    }
+    if (np > 1) {
+        p->scratch = (cd*)fftb200_malloc(sizeof(cd) * ((size_t)p->batch << L));
+        if (!p->scratch) return -1;
+    }
+    return 0;
+}
+
+// Enqueue the power-of-two c2c passes: `inverse` selects conjugated twiddles and the 1/m scale.
+static int enqueue_c2c(fftb200_plan* p, const cd* in, cd* out, int inverse) {
+    for (const Pass& ps : p->passes) {
+        TileArgs a;
+        const cd* src = ps.src == BUF_IN ? in : ps.src == BUF_OUT ? out : p->scratch;
+        cd* dst = ps.dst == BUF_OUT ? out : p->scratch;
+        a.in = src; a.out = dst; a.tab = p->tab;
+        a.ntiles = ps.ntiles; a.batch = p->batch;
+        a.log_n = p->log_n; a.log_m = ps.log_m;
+        a.inverse = inverse; a.scale = 1.0 / (double)p->m; a.final_pass = ps.final_pass;
+        ps.k->launch(a, ps.grid, p->stream);
+    }
+    CU(cudaGetLastError());
+    return 0;
+}
+
+static int upload_table(fftb200_plan* p, DeviceState* ds, const fftb200_plan_desc* d, int need_n) {
+    if (need_n <= 1) { p->tab = nullptr; return 0; }
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (ds->tab && ds->tab_n >= need_n) { p->tab = ds->tab; return 0; }
+    if (!d->twiddles || d->table_n < need_n) return fail("plan needs a twiddle table for size %d", need_n);
+    cd* t = nullptr;
+    size_t bytes = sizeof(cd) * (size_t)(d->table_n - 1);
+    CU(cudaMalloc(&t, bytes ? bytes : 16));
+    CU(cudaMemcpy(t, d->twiddles, bytes, cudaMemcpyHostToDevice));
+    CU(cudaStreamSynchronize(cudaStreamLegacy));
+    if (ds->tab) ds->old.push_back(ds->tab);  // plans created earlier still point at it
+    ds->tab = t;
+    ds->tab_n = d->table_n;
+    p->tab = t;
+    return 0;
+}
+
+extern "C" int fftb200_plan_create(fftb200_plan** out, const fftb200_plan_desc* d) {
+    if (!out || !d) return fail("plan_create: null argument");
+    *out = nullptr;
+    if (d->n <= 0 || d->batch <= 0) return fail("plan_create: n and batch must be positive");
+    if (d->direction != -1 && d->direction != 1) return fail("plan_create: direction must be -1 or +1");
+    DeviceState* ds;
+    if (cur_device(&ds) != 0) return -1;
+    fftb200_plan* p = new fftb200_plan();
+    p->device = fftb200_get_device();
+    p->n = d->n; p->batch = d->batch; p->dir = d->direction; p->kind = d->kind;
+    const bool pow2 = (d->n & (d->n - 1)) == 0;
+    int rc = 0;
+    do {
+        if (d->kind == FFTB200_C2C || d->kind == FFTB200_R2C) {
+            if (!pow2) { rc = fail("plan_create: kind %d needs a power-of-two n (got %d)", d->kind, d->n); break; }
+            p->m = d->n;
+        } else if (d->kind == FFTB200_BLUESTEIN) {
+            long long m = 1;
+            while (m < 2LL * d->n - 1) m <<= 1;
+            if (m > (1LL << 30)) { rc = fail("plan_create: Bluestein length too large"); break; }
+            p->m = (int)m;
+            if (!d->chirp) { rc = fail("plan_create: Bluestein needs a host chirp table"); break; }
+        } else { rc = fail("plan_create: unknown kind %d", d->kind); break; }
+        p->log_n = ilog2(p->m);
+        if ((rc = cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking)) != 0) { rc = fail("cudaStreamCreate failed"); break; }
+        if (cudaStreamCreateWithFlags(&p->stream2, cudaStreamNonBlocking) != cudaSuccess) { rc = fail("cudaStreamCreate failed"); break; }
+        if (cudaEventCreate(&p->ev0) != cudaSuccess || cudaEventCreate(&p->ev1) != cudaSuccess) { rc = fail("cudaEventCreate failed"); break; }
+        if ((rc = upload_table(p, ds, d, p->m)) != 0) break;
+        char head[96];
+        snprintf(head, sizeof(head), "%s n=%d b=%d dir=%d: ", d->kind == FFTB200_C2C ? "c2c" : d->kind == FFTB200_R2C ? "r2c" : "bluestein", d->n, d->batch, d->direction);
+        p->desc = head;
+        if ((rc = build_passes(p, ds)) != 0) break;
+        p->launches = (int)p->passes.size();
+        if (d->kind == FFTB200_R2C) {
+            p->work = (cd*)fftb200_malloc(sizeof(cd) * (size_t)p->m * (size_t)p->batch);
+            if (!p->work) { rc = -1; break; }
+            p->launches += 2;
+        }
+        if (d->kind == FFTB200_BLUESTEIN) {
+            const size_t m = (size_t)p->m;
+            p->work = (cd*)fftb200_malloc(sizeof(cd) * m * (size_t)p->batch);
+            p->chirp = (cd*)fftb200_malloc(sizeof(cd) * (size_t)p->n);
+            p->fb = (cd*)fftb200_malloc(sizeof(cd) * m);
+            if (!p->work || !p->chirp || !p->fb) { rc = -1; break; }
+            if (cudaMemcpy(p->chirp, d->chirp, sizeof(cd) * (size_t)p->n, cudaMemcpyHostToDevice) != cudaSuccess ||
+                cudaStreamSynchronize(cudaStreamLegacy) != cudaSuccess) { rc = fail("chirp upload failed"); break; }
+            // b[k] = chirp[k], b[m-k] = chirp[k] (bluestein.c:116-121); FB = FFT_m(b), cached in the plan.
+            // The sub-plan is built for the whole batch; a single-transform view of it computes FB.
+            {
+                const int save_batch = p->batch;
+                std::vector<Pass> save = p->passes;
+                cd* save_scratch = p->scratch;
+                p->batch = 1; p->passes.clear(); p->scratch = nullptr; std::string sd = p->desc;
+                rc = build_passes(p, ds);
+                if (rc == 0) {
+                    bluestein_wrap_kernel<<<(unsigned)((m + 255) / 256), 256, 0, p->stream>>>(p->fb, p->chirp, p->n, p->m);
+                    rc = enqueue_c2c(p, p->fb, p->fb, 0);
+                    if (rc == 0 && cudaStreamSynchronize(p->stream) != cudaSuccess) rc = fail("Bluestein kernel spectrum failed: %s", cudaGetErrorString(cudaGetLastError()));
+                }
+                if (p->scratch) cudaFree(p->scratch);
+                p->batch = save_batch; p->passes = save; p->scratch = save_scratch; p->desc = sd;
+                if (rc != 0) break;
+            }
+            p->launches = 2 * (int)p->passes.size() + 3;
+        }
+    } while (0);
+    if (rc != 0) { fftb200_plan_destroy(p); return -1; }
+    *out = p;
+    return 0;
+}
+
+extern "C" int fftb200_plan_exec_async(fftb200_plan* p, const void* d_in, void* d_out) {
+    if (!p || !d_in || !d_out) return fail("plan_exec: null argument");
+    const int inverse = p->dir > 0;
+    if (p->kind == FFTB200_C2C) return enqueue_c2c(p, (const cd*)d_in, (cd*)d_out, inverse);
+    const size_t m = (size_t)p->m, n = (size_t)p->n, total = m * (size_t)p->batch;
+    unsigned blocks = (unsigned)((total + 255) / 256 > (1u << 20) ? (1u << 20) : (total + 255) / 256);
+    if (p->kind == FFTB200_R2C) {
+        r2c_promote_kernel<<<blocks, 256, 0, p->stream>>>(p->work, (const double*)d_in, total);
+        if (enqueue_c2c(p, p->work, p->work, 0) != 0) return -1;
+        const size_t nh = n / 2 + 1, tot_out = nh * (size_t)p->batch;
+        unsigned b2 = (unsigned)((tot_out + 255) / 256 > (1u << 20) ? (1u << 20) : (tot_out + 255) / 256);
+        r2c_extract_kernel<<<b2, 256, 0, p->stream>>>((cd*)d_out, p->work, n, nh, tot_out);
+        CU(cudaGetLastError());
+        return 0;
+    }
+    // Bluestein (bluestein.c:107-148): a = x * conj(chirp) zero-padded to m; A = FFT(a) * FB; inverse FFT;
+    // y = a * conj(chirp) (and 1/n for the inverse direction).
+    bluestein_pre_kernel<<<blocks, 256, 0, p->stream>>>(p->work, (const cd*)d_in, p->chirp, p->n, p->m, total);
+    if (enqueue_c2c(p, p->work, p->work, 0) != 0) return -1;
+    pointwise_mul_kernel<<<blocks, 256, 0, p->stream>>>(p->work, p->work, p->fb, total, m);
+    if (enqueue_c2c(p, p->work, p->work, 1) != 0) return -1;
+    const size_t tot_out = n * (size_t)p->batch;
+    unsigned b2 = (unsigned)((tot_out + 255) / 256 > (1u << 20) ? (1u << 20) : (tot_out + 255) / 256);
+    bluestein_post_kernel<<<b2, 256, 0, p->stream>>>((cd*)d_out, p->work, p->chirp, p->n, p->m, tot_out,
+                                                      inverse ? 1.0 / (double)p->n : 1.0);
+    CU(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int fftb200_plan_sync(fftb200_plan* p) {
+    if (!p) return fail("plan_sync: null plan");
+    CU(cudaStreamSynchronize(p->stream));
+    return 0;
+}
+
+extern "C" int fftb200_plan_exec(fftb200_plan* p, const void* d_in, void* d_out) {
+    if (fftb200_plan_exec_async(p, d_in, d_out) != 0) return -1;
+    return fftb200_plan_sync(p);
+}
+
+// Host-pointer execution (the H2D -> execute -> D2H sequence of algorithms/auto/fft_auto.c:278-280 and
+// gpu/fft_cuda.cu:214-252). Device staging buffers live in the plan.
+extern "C" int fftb200_plan_exec_host(fftb200_plan* p, const void* h_in, void* h_out) {
+    if (!p || !h_in || !h_out) return fail("plan_exec_host: null argument");
+    const size_t in_bytes = (p->kind == FFTB200_R2C ? sizeof(double) : sizeof(cd)) * (size_t)p->n * (size_t)p->batch;
+    const size_t out_elems = (p->kind == FFTB200_R2C ? (size_t)(p->n / 2 + 1) : (size_t)p->n) * (size_t)p->batch;
+    if (!p->d_stage_in) {
+        p->d_stage_in = (cd*)fftb200_malloc(in_bytes > out_elems * sizeof(cd) ? in_bytes : out_elems * sizeof(cd));
+        if (!p->d_stage_in) return -1;
+    }
+    void* d_out = p->d_stage_in;
+    if (p->kind == FFTB200_R2C) {
+        if (!p->d_stage_out) { p->d_stage_out = (cd*)fftb200_malloc(out_elems * sizeof(cd)); if (!p->d_stage_out) return -1; }
+        d_out = p->d_stage_out;
+    }
+    CU(cudaMemcpyAsync(p->d_stage_in, h_in, in_bytes, cudaMemcpyHostToDevice, p->stream));
+    if (fftb200_plan_exec_async(p, p->d_stage_in, d_out) != 0) return -1;
+    CU(cudaMemcpyAsync(h_out, d_out, out_elems * sizeof(cd), cudaMemcpyDeviceToHost, p->stream));
+    CU(cudaStreamSynchronize(p->stream));
+    return 0;
+}
+
+extern "C" void fftb200_plan_destroy(fftb200_plan* p) {
+    if (!p) return;
+    if (p->stream) cudaStreamSynchronize(p->stream);
+    if (p->scratch) cudaFree(p->scratch);
+    if (p->work) cudaFree(p->work);
+    if (p->chirp) cudaFree(p->chirp);
+    if (p->fb) cudaFree(p->fb);
+    if (p->d_stage_in) cudaFree(p->d_stage_in);
+    if (p->d_stage_out) cudaFree(p->d_stage_out);
+    if (p->ev0) cudaEventDestroy(p->ev0);
+    if (p->ev1) cudaEventDestroy(p->ev1);
+    if (p->stream) cudaStreamDestroy(p->stream);
+    if (p->stream2) cudaStreamDestroy(p->stream2);
+    delete p;
+}
+
+extern "C" int fftb200_plan_launches(const fftb200_plan* p) { return p ? p->launches : 0; }
+extern "C" const char* fftb200_plan_describe(const fftb200_plan* p) { return p ? p->desc.c_str() : ""; }
+
+extern "C" int fftb200_timer_start(fftb200_plan* p) {
+    if (!p) return fail("timer: null plan");
+    CU(cudaEventRecord(p->ev0, p->stream));
+    return 0;
+}
+extern "C" int fftb200_timer_stop(fftb200_plan* p, float* ms) {
+    if (!p || !ms) return fail("timer: null argument");
+    CU(cudaEventRecord(p->ev1, p->stream));
+    CU(cudaEventSynchronize(p->ev1));
+    CU(cudaEventElapsedTime(ms, p->ev0, p->ev1));
+    return 0;
+}

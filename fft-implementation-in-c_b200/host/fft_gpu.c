@@ -1,0 +1,172 @@
+/*
+ * fft_gpu.c - the public device API (include/fft_gpu.h) as a thin C99 launcher over the engine's
+ * C-ABI (include/fftb200.h).
+ *
+ * Replaces the reference's gpu/fft_gpu.c (a switch over backends whose CUDA branches are compiled out
+ * under gcc, so fft_gpu_available() is constant 0 on Linux) and its callee gpu/fft_cuda.cu. Same
+ * signatures and error conventions: constructors return NULL, int functions 0 / -1, void functions
+ * silently ignore NULL handles (reference gpu/fft_gpu.c:247), errors print one line on stderr
+ * (reference gpu/fft_cuda.cu:34-50). Nothing here computes on the CPU.
+ */
+#include "../../include/fft_gpu.h"
+#include "../../include/fftb200.h"
+#include "ref_twiddle.h"
+
+struct fft_gpu_memory {
+    void* dptr;
+    size_t size; /* complex elements */
+};
+
+struct fft_gpu_plan {
+    fftb200_plan* engine;
+    int n, batch;
+    fft_direction direction;
+};
+
+static fft_gpu_backend_t g_backend = FFT_GPU_NONE;
+
+static void report(const char* what) { fprintf(stderr, "fft_gpu: %s: %s\n", what, fftb200_last_error()); }
+
+int fft_gpu_available(void) { return fftb200_device_count() > 0 ? 1 : 0; }
+
+int fft_gpu_init(fft_gpu_backend_t backend) {
+    if (backend != FFT_GPU_CUDA && backend != FFT_GPU_AUTO) return -1; /* Metal / OpenCL: not on this platform */
+    if (g_backend == FFT_GPU_CUDA) return 0;                          /* idempotent, reference fft_cuda.cu:54 */
+    if (!fft_gpu_available()) return -1;
+    const char* dev = getenv("FFTB200_DEVICE");
+    if (dev && fftb200_set_device(atoi(dev)) != 0) { report("set device"); return -1; }
+    g_backend = FFT_GPU_CUDA;
+    return 0;
+}
+
+void fft_gpu_cleanup(void) {
+    if (g_backend == FFT_GPU_CUDA) fftb200_device_reset();
+    g_backend = FFT_GPU_NONE;
+}
+
+fft_gpu_backend_t fft_gpu_get_backend(void) { return g_backend; }
+
+static int ensure_init(void) { return g_backend == FFT_GPU_CUDA ? 0 : fft_gpu_init(FFT_GPU_AUTO); }
+
+fft_gpu_memory_t fft_gpu_alloc(size_t size) {
+    if (ensure_init() != 0) return NULL;
+    fft_gpu_memory_t m = (fft_gpu_memory_t)malloc(sizeof(*m));
+    if (!m) return NULL;
+    m->dptr = fftb200_malloc(size * sizeof(complex_t));
+    if (!m->dptr) { report("alloc"); free(m); return NULL; }
+    m->size = size;
+    return m;
+}
+
+void fft_gpu_free(fft_gpu_memory_t mem) {
+    if (!mem) return;
+    fftb200_free(mem->dptr);
+    free(mem);
+}
+
+void fft_gpu_copy_h2d(fft_gpu_memory_t dst, const complex_t* src, size_t size) {
+    if (!dst || !src) return;
+    if (size > dst->size) size = dst->size;
+    if (fftb200_memcpy_h2d(dst->dptr, src, size * sizeof(complex_t)) != 0) report("copy_h2d");
+}
+
+void fft_gpu_copy_d2h(complex_t* dst, fft_gpu_memory_t src, size_t size) {
+    if (!dst || !src) return;
+    if (size > src->size) size = src->size;
+    if (fftb200_memcpy_d2h(dst, src->dptr, size * sizeof(complex_t)) != 0) report("copy_d2h");
+}
+
+/* shared with fft_auto.c: build an engine plan of the given kind for (n, batch, direction) */
+fftb200_plan* fftb200_host_make_plan(int n, int batch, int direction, int kind) {
+    if (n <= 0 || batch <= 0) return NULL;
+    if (ensure_init() != 0) return NULL;
+    fftb200_plan_desc d;
+    memset(&d, 0, sizeof(d));
+    d.n = n; d.batch = batch; d.direction = direction < 0 ? -1 : 1; d.kind = kind;
+    double* chirp = NULL;
+    if (kind == FFTB200_BLUESTEIN) {
+        long long m = 1;
+        while (m < 2LL * n - 1) m <<= 1;
+        if (m > (1LL << 30)) return NULL;
+        d.table_n = (int)m;
+        chirp = (double*)malloc(sizeof(double) * 2 * (size_t)n);
+        if (!chirp) return NULL;
+        fftb200_host_chirp(chirp, n, d.direction);
+        d.chirp = chirp;
+    } else {
+        d.table_n = n;
+    }
+    d.twiddles = fftb200_host_twiddles(d.table_n);
+    fftb200_plan* p = NULL;
+    if (!d.twiddles || fftb200_plan_create(&p, &d) != 0) { report("plan"); p = NULL; }
+    free(chirp);
+    return p;
+}
+
+fft_gpu_plan_t fft_gpu_plan_1d(int n, int batch, fft_direction direction) {
+    if (n <= 0 || batch <= 0) return NULL;
+    fft_gpu_plan_t p = (fft_gpu_plan_t)malloc(sizeof(*p));
+    if (!p) return NULL;
+    p->engine = fftb200_host_make_plan(n, batch, (int)direction, is_power_of_two(n) ? FFTB200_C2C : FFTB200_BLUESTEIN);
+    if (!p->engine) { free(p); return NULL; }
+    p->n = n; p->batch = batch; p->direction = direction;
+    return p;
+}
+
+void fft_gpu_execute(fft_gpu_plan_t plan, fft_gpu_memory_t in, fft_gpu_memory_t out) {
+    if (!plan || !in || !out) return;
+    const size_t need = (size_t)plan->n * (size_t)plan->batch;
+    if (in->size < need || out->size < need) { fprintf(stderr, "fft_gpu: execute: buffer smaller than n*batch\n"); return; }
+    if (fftb200_plan_exec(plan->engine, in->dptr, out->dptr) != 0) report("execute");
+}
+
+void fft_gpu_destroy_plan(fft_gpu_plan_t plan) {
+    if (!plan) return;
+    fftb200_plan_destroy(plan->engine);
+    free(plan);
+}
+
+int fft_gpu_dft_1d_batch(complex_t* in, complex_t* out, int n, int batch, fft_direction direction) {
+    if (!in || !out || n <= 0 || batch <= 0) return -1;
+    fftb200_plan* p = fftb200_host_make_plan(n, batch, (int)direction, is_power_of_two(n) ? FFTB200_C2C : FFTB200_BLUESTEIN);
+    if (!p) return -1;
+    int rc = fftb200_plan_exec_host(p, in, out);
+    if (rc != 0) report("dft_1d_batch");
+    fftb200_plan_destroy(p);
+    return rc == 0 ? 0 : -1;
+}
+
+int fft_gpu_dft_1d(complex_t* in, complex_t* out, int n, fft_direction direction) {
+    return fft_gpu_dft_1d_batch(in, out, n, 1, direction);
+}
+
+/* 2-D: stubs in the reference (gpu/fft_gpu.c:377-394) */
+fft_gpu_plan_t fft_gpu_plan_2d(int rows, int cols, fft_direction direction) {
+    (void)rows; (void)cols; (void)direction;
+    return NULL;
+}
+int fft_gpu_dft_2d(complex_t* in, complex_t* out, int rows, int cols, fft_direction direction) {
+    (void)in; (void)out; (void)rows; (void)cols; (void)direction;
+    return -1;
+}
+
+const char* fft_gpu_get_device_name(void) {
+    if (ensure_init() != 0) return "No GPU";
+    return fftb200_device_name();
+}
+
+void fft_gpu_get_memory_info(size_t* total, size_t* available) {
+    size_t f = 0, t = 0;
+    if (ensure_init() == 0) fftb200_mem_info(&f, &t);
+    if (total) *total = t;
+    if (available) *available = f;
+}
+
+int fft_gpu_set_device(int device) {
+    if (!fft_gpu_available()) return -1;
+    return fftb200_set_device(device) == 0 ? 0 : -1;
+}
+
+/* engine handle of a public plan, for the additive helpers in fftb200_ext.h (timing, async) */
+fftb200_plan* fftb200_engine_of(fft_gpu_plan_t plan) { return plan ? plan->engine : NULL; }
+void* fftb200_devptr_of(fft_gpu_memory_t mem) { return mem ? mem->dptr : NULL; }

@@ -1,0 +1,126 @@
+/*
+ * ref_twiddle.c - twiddle and chirp tables that make the GPU transform reproduce the reference's
+ * numbers, not just the mathematically exact DFT.
+ *
+ * The reference never tabulates twiddles: inside every stage it advances w <- w * w_m serially
+ * (algorithms/core/radix2_dit.c:93,109; same loop in radix4.c:110-125 and split_radix.c:39-54), with
+ * w_m = twiddle_factor(1, m, dir) (include/fft_common.h:89-98). The rounded root w_m is raised to
+ * powers up to m/2, so its rounding error grows linearly along the stage: the reference is off from
+ * the exact DFT by 9e-12 (relative L2) at N = 2^20 and 1.6e-10 at 2^24 - far more than the 1e-12
+ * parity bar. The kernels therefore read w from a table built here by the same recurrence.
+ *
+ * Bit-faithfulness: the reference is built with -O3 -ffast-math and FMA contraction (its Makefile:7).
+ * gcc 13 compiles `w *= w_m` to
+ *      re' = fma(re, m_re, -(im * m_im))        im' = fma(re, m_im, im * m_re)
+ * (disassembly of radix2_dit_fft in oracle/_ref/libfftref.so), and cexp(I*angle) to sincos(angle).
+ * That sequence is written out explicitly below and THIS FILE IS COMPILED WITHOUT -ffast-math and with
+ * -ffp-contract=off, so the compiler cannot re-associate or re-contract it. tests/test_oracle.py checks
+ * the tables bit-for-bit against the oracle's recurrence.
+ *
+ * Likewise the Bluestein chirp phase -dir*PI*k*k/n (algorithms/core/bluestein.c:59-62) is evaluated by
+ * the reference's build as (k*k) * ((-dir*PI) * (1/n)); at n ~ 1e6 the phase is ~3e6 rad, so a
+ * different association changes the result at the 1e-10 level. It is written out the same way here.
+ */
+#define _GNU_SOURCE
+#include "ref_twiddle.h"
+
+#include <math.h>
+#include <pthread.h>
+#include <stdlib.h>
+#include <string.h>
+
+#define REF_PI 3.14159265358979323846 /* include/fft_common.h:24 of the reference */
+
+static pthread_mutex_t g_mu = PTHREAD_MUTEX_INITIALIZER;
+static double* g_tab = NULL; /* interleaved, (g_n - 1) complex */
+static int g_n = 0;
+static int g_mode = -1;      /* 0 reference recurrence, 1 accurate */
+static double* g_old[40];    /* superseded (smaller) tables: plans created earlier may still read them */
+static int g_nold = 0;
+
+int fftb200_host_twiddle_mode_accurate(void) {
+    if (g_mode < 0) {
+        const char* e = getenv("FFTB200_TWIDDLE");
+        g_mode = (e && strcmp(e, "accurate") == 0) ? 1 : 0;
+    }
+    return g_mode;
+}
+
+/* stage root for the forward direction: twiddle_factor(1, m, FFT_FORWARD) */
+static void stage_root(int m, double* re, double* im) {
+    if (m == 2) { *re = -1.0; *im = 0.0; return; }
+    if (m == 4) { *re = 0.0; *im = -1.0; return; }
+    double angle = (-1.0 * (2.0 * REF_PI)) * 1.0 / (double)m;
+    double s, c;
+    sincos(angle, &s, &c);
+    *re = c; *im = s;
+}
+
+static void fill_stage(double* t, int s) {
+    const int half = 1 << (s - 1);
+    if (fftb200_host_twiddle_mode_accurate()) {
+        for (int j = 0; j < half; j++) {
+            long double a = -2.0L * 3.14159265358979323846264338327950288L * (long double)j / (long double)(2 * half);
+            t[2 * j] = (double)cosl(a);
+            t[2 * j + 1] = (double)sinl(a);
+        }
+        return;
+    }
+    double mr, mi, wr = 1.0, wi = 0.0;
+    stage_root(2 * half, &mr, &mi);
+    for (int j = 0; j < half; j++) {
+        t[2 * j] = wr;
+        t[2 * j + 1] = wi;
+        const double p_im_mi = wi * mi, p_im_mr = wi * mr;
+        const double nr = fma(wr, mr, -p_im_mi);
+        const double ni = fma(wr, mi, p_im_mr);
+        wr = nr; wi = ni;
+    }
+}
+
+const double* fftb200_host_twiddles(int n) {
+    if (n < 1 || (n & (n - 1))) return NULL;
+    pthread_mutex_lock(&g_mu);
+    if (g_n < n) {
+        double* t = (double*)malloc(sizeof(double) * 2 * (size_t)(n > 1 ? n - 1 : 1));
+        if (!t) { pthread_mutex_unlock(&g_mu); return NULL; }
+        int have = 0;
+        if (g_tab && g_n > 1) { memcpy(t, g_tab, sizeof(double) * 2 * (size_t)(g_n - 1)); have = g_n; }
+        for (int s = 1; (1 << s) <= n && s < 31; s++) {
+            if ((1 << s) <= have) continue;
+            fill_stage(t + 2 * ((size_t)(1 << (s - 1)) - 1), s);
+        }
+        /* Superseded tables stay allocated until release: a plan being created on another thread may
+         * still be uploading from one. They are prefixes of the new table, at most as large in total. */
+        if (g_tab && g_nold < 40) g_old[g_nold++] = g_tab;
+        g_tab = t;
+        g_n = n;
+    }
+    const double* r = g_tab;
+    pthread_mutex_unlock(&g_mu);
+    return r;
+}
+
+void fftb200_host_tables_release(void) {
+    pthread_mutex_lock(&g_mu);
+    for (int i = 0; i < g_nold; i++) free(g_old[i]);
+    g_nold = 0;
+    free(g_tab);
+    g_tab = NULL;
+    g_n = 0;
+    pthread_mutex_unlock(&g_mu);
+}
+
+void fftb200_host_chirp(double* out, int n, int dir) {
+    const double scale = (double)(-dir) * REF_PI;
+    const double rn = 1.0 / (double)n;
+    const double c0 = scale * rn;
+    for (int k = 0; k < n; k++) {
+        const double k2 = (double)k * (double)k;
+        const double phase = k2 * c0;
+        double s, c;
+        sincos(phase, &s, &c);
+        out[2 * k] = c;
+        out[2 * k + 1] = s;
+    }
+}

@@ -1,0 +1,96 @@
+/*
+ * fftb200.h - C-ABI of the B200 (sm_100a) FFT engine: the boundary between the C99 host library
+ * (fft_auto.c / fft_gpu.c, which keep the reference's public API) and the hand-written CUDA kernels.
+ *
+ * Plain pointers and sizes only: no C99 _Complex, no C++ or torch types. Complex data is interleaved
+ * (re, im) doubles, byte-compatible with the reference's complex_t (include/fft_common.h:28 there) and
+ * with CUDA's double2.
+ *
+ * Each entry point names the reference interface it replaces (paths relative to the reference tree):
+ *   device lifecycle      gpu/fft_cuda.cu:53-101   fft_gpu_init_cuda / cleanup / available
+ *   memory + copies       gpu/fft_cuda.cu:103-135  fft_gpu_alloc_cuda / free / copy_h2d / copy_d2h
+ *   plan create / destroy gpu/fft_cuda.cu:138-163, 188-197  (cufftPlan1d / cufftPlanMany / cufftDestroy)
+ *   plan exec             gpu/fft_cuda.cu:166-185  (cufftExecZ2Z + cudaDeviceSynchronize)
+ *   bluestein / r2c kinds algorithms/core/bluestein.c:79-155, algorithms/auto/fft_auto.c:391-403
+ *
+ * All functions returning int give 0 on success and a negative value on failure; the message is
+ * available from fftb200_last_error(). Nothing here falls back to the CPU.
+ */
+#ifndef FFTB200_H
+#define FFTB200_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct fftb200_plan fftb200_plan;
+
+enum fftb200_kind {
+    FFTB200_C2C = 0,       /* power-of-two complex transform                                  */
+    FFTB200_BLUESTEIN = 1, /* arbitrary n through a padded power-of-two circular convolution  */
+    FFTB200_R2C = 2        /* real input, n/2 + 1 complex outputs, power-of-two n             */
+};
+
+typedef struct fftb200_plan_desc {
+    int n;                  /* transform length                                                          */
+    int batch;              /* transforms per execution; transform b occupies [b*n, (b+1)*n)             */
+    int direction;          /* -1 forward (unscaled), +1 inverse (scaled by 1/n)                         */
+    int kind;               /* enum fftb200_kind                                                         */
+    const double* twiddles; /* HOST, forward stage tables for size `table_n` (table_n - 1 complex):      */
+                            /* entry (stage s, j) at 2^(s-1) - 1 + j. table_n = n, or Bluestein's m      */
+    int table_n;
+    const double* chirp;    /* HOST, n complex, Bluestein only: chirp for `direction`                    */
+    unsigned flags;         /* reserved                                                                  */
+} fftb200_plan_desc;
+
+/* ---- device ---- */
+int fftb200_device_count(void);              /* number of CUDA devices, 0 when none / no driver   */
+int fftb200_set_device(int device);
+int fftb200_get_device(void);
+const char* fftb200_device_name(void);       /* name of the current device                        */
+int fftb200_mem_info(size_t* free_bytes, size_t* total_bytes);
+int fftb200_sm_count(void);
+int fftb200_device_reset(void);              /* drops cached tables of the current device         */
+
+/* ---- memory ---- */
+void* fftb200_malloc(size_t bytes);          /* device memory, NULL on failure                    */
+void fftb200_free(void* dptr);
+void* fftb200_host_alloc(size_t bytes);      /* pinned host memory for staging                    */
+void fftb200_host_free(void* hptr);
+int fftb200_memcpy_h2d(void* dst, const void* src, size_t bytes);   /* synchronous               */
+int fftb200_memcpy_d2h(void* dst, const void* src, size_t bytes);   /* synchronous               */
+int fftb200_memcpy_d2d(void* dst, const void* src, size_t bytes);
+int fftb200_memset(void* dst, int value, size_t bytes);
+int fftb200_fill_splitmix(void* dst, unsigned long long seed, unsigned long long first_elem,
+                          unsigned long long count);  /* synthetic input generated on the device */
+
+/* ---- plans ---- */
+int fftb200_plan_create(fftb200_plan** out, const fftb200_plan_desc* desc);
+/* d_in / d_out are device pointers (complex; R2C: d_in is n*batch doubles, d_out (n/2+1)*batch complex).
+ * In place (d_in == d_out) is allowed for C2C and BLUESTEIN. Returns after the result is visible. */
+int fftb200_plan_exec(fftb200_plan* plan, const void* d_in, void* d_out);
+/* Same, but only enqueues on the plan's stream. */
+int fftb200_plan_exec_async(fftb200_plan* plan, const void* d_in, void* d_out);
+int fftb200_plan_sync(fftb200_plan* plan);
+/* Host-pointer execution: pinned staging, chunked H2D / kernels / D2H overlapped on two streams. */
+int fftb200_plan_exec_host(fftb200_plan* plan, const void* h_in, void* h_out);
+void fftb200_plan_destroy(fftb200_plan* plan);
+int fftb200_plan_launches(const fftb200_plan* plan);     /* kernel launches per execution         */
+const char* fftb200_plan_describe(const fftb200_plan* plan); /* e.g. "c2c n=4096 b=65536: C12"    */
+
+/* ---- timing on the plan's stream (CUDA events) ---- */
+int fftb200_timer_start(fftb200_plan* plan);
+int fftb200_timer_stop(fftb200_plan* plan, float* elapsed_ms);   /* synchronises on the stop event */
+
+/* ---- elementwise helpers used by the callers either side of the transform ---- */
+/* y[i] = a[i] * b[i], count complex elements (FFT convolution, Bluestein's frequency-domain product) */
+int fftb200_pointwise_mul(void* d_y, const void* d_a, const void* d_b, size_t count);
+
+const char* fftb200_last_error(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FFTB200_H */
