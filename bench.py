@@ -1,0 +1,355 @@
+#!/usr/bin/env python
+"""bench.py - headline benchmark of the B200 FFT hot path (BASELINE.json: batched c2c double FFT,
+GFLOP/s = 5*N*log2(N)*batch / t, plus the fraction of the HBM roofline).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]          our arm (CUDA kernels through the C ABI)
+  python bench.py --impl reference [--gpus N] ...              the reference's own CPU code on the host cores
+  python bench.py --sweep                                      extra: table over N = 2^6 .. 2^24 (not a bench line)
+
+A step is one execution of the batched plan over the whole synthetic input (default workload
+BASELINE.json configs[1]: N = 4096 x batch 65536 per GPU, 4 GiB in + 4 GiB out). The input is generated
+on the device (counter-based splitmix64 stream) and is resident in HBM when the timed region
+starts; it is 32x larger than L2, so no flush is needed between iterations. Timing: CUDA events on the
+plan's stream around exactly K executions, barrier + device sync on both sides, max over ranks.
+Multi-GPU (torchrun, one process per GPU): transforms are independent, so every rank owns a full
+per-GPU batch (weak scaling) and there is no collective on the data path.
+
+`e2e` is the same metric through the reference-facing host-pointer call fft_gpu_dft_1d_batch(in, out, n,
+batch, dir) on buffers from fft_alloc_complex: H2D and D2H copies are inside the timed region.
+
+Only the cpu_baseline / --impl reference legs touch oracle/ (the reference compiled into oracle/_ref, or
+the C restatement when that is absent). Nothing here reads /root/reference.
+"""
+import argparse
+import ctypes as C
+import json
+import math
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+FALLBACK_HBM_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md fallback when MEASURED_PEAKS.json is absent
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--n", type=int, default=4096)
+    ap.add_argument("--batch", type=int, default=65536, help="transforms per GPU")
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--cpu-sample", type=int, default=16384, help="transforms per CPU step")
+    ap.add_argument("--sweep", action="store_true")
+    return ap.parse_args()
+
+
+def hbm_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        d = json.load(open(path))
+        for k in ("hbm_gbs", "hbm_copy_gbs", "hbm_gb_s"):
+            if k in d:
+                return float(d[k]), "measured (MEASURED_PEAKS.json %s)" % k
+    except Exception:
+        pass
+    return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.06)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, pw, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [s.strip() for s in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1])); pw.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "power_w": round(statistics.median(pw), 1),
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def flops(n, batch):
+    return 5.0 * n * math.log2(n) * batch
+
+
+# --------------------------------------------------------------------------------------------------
+# reference arm: the reference's CPU implementation on the host cores
+# --------------------------------------------------------------------------------------------------
+def cpu_reference(n, sample, steps, warmup):
+    """Times the reference CPU path over `sample` transforms of length n per step, all host cores.
+    Returns (gflops, seconds_per_step, kind, cores, description)."""
+    import numpy as np
+    from oracle import oracle as O
+    cores = os.cpu_count() or 1
+    p = O.port()
+    x = p.fill(43, 0, n * sample).reshape(sample, n)
+    out = np.empty_like(x)
+    kind = "port"
+    run = None
+    pow2 = (n & (n - 1)) == 0
+    try:
+        par = O.par()
+        run = lambda: par.batch_execute(x, out, -1, cores)
+        kind = "reference"
+        desc = ("unmodified reference fft_plan_dft_1d/fft_execute_dft (oracle/_ref/libfftref.so), one plan per thread, "
+                "%d threads, %d transforms of N=%d per step" % (cores, sample, n))
+    except Exception:
+        if not pow2:
+            raise
+        def run():
+            out[...] = x
+            return p.fft_batch_inplace(out, -1, cores)
+        desc = "C restatement oracle_fft_pow2_batch, %d OpenMP threads, %d transforms of N=%d per step" % (cores, sample, n)
+    for _ in range(warmup):
+        run()
+    ts = []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        rc = run()
+        ts.append(time.perf_counter() - t0)
+        if rc != 0:
+            raise RuntimeError("CPU reference failed")
+    t = sum(ts) / len(ts)
+    return flops(n, sample) / t * 1e-9, t, kind, cores, desc
+
+
+def main_reference(args, rank, world):
+    if rank != 0:
+        return
+    steps = max(1, min(args.steps, 20))
+    gf, t, kind, cores, desc = cpu_reference(args.n, args.cpu_sample, steps, min(args.warmup, 2))
+    line = {
+        "impl": "reference", "metric": "batched c2c double FFT GFLOP/s (5*N*log2N*batch/t)", "value": gf, "unit": "GFLOP/s",
+        "n_gpus": args.gpus, "steps": steps, "warmup": min(args.warmup, 2), "ms_per_step": t * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic (splitmix64 stream, seed 43)",
+        "config": {"workload": "batched c2c double FFT N=%d x %d batch per GPU" % (args.n, args.batch),
+                   "n": args.n, "batch_per_gpu": args.batch, "direction": "forward",
+                   "note": "CPU arm runs a bounded sample of the batch per step; throughput is per transform, so it extrapolates"},
+        "cpu_baseline": {"value": gf, "unit": "GFLOP/s", "cores": cores, "kind": kind, "sample": desc},
+        "e2e": {"value": gf, "unit": "GFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------------
+# our arm
+# --------------------------------------------------------------------------------------------------
+def time_plan(L, eng, din, dout, steps, warmup, sync=None):
+    for _ in range(warmup):
+        if L.fftb200_plan_exec(eng, din, dout) != 0:
+            raise RuntimeError(L.fftb200_last_error().decode())
+    ms = C.c_float()
+    if sync:
+        sync()
+    L.fftb200_timer_start(eng)
+    for _ in range(steps):
+        L.fftb200_plan_exec_async(eng, din, dout)
+    if L.fftb200_timer_stop(eng, C.byref(ms)) != 0:
+        raise RuntimeError(L.fftb200_last_error().decode())
+    if sync:
+        sync()
+    return ms.value / steps
+
+
+def main_b200(args, rank, world, local_rank):
+    import fftb200_loader
+    F = fftb200_loader.load()
+    L = F.lib
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    if L.fft_gpu_available() != 1:
+        raise SystemExit("bench.py: no CUDA device - the B200 path has no CPU fallback")
+    if L.fft_gpu_set_device(local_rank) != 0 or L.fft_gpu_init(F.FFT_GPU_AUTO) != 0:
+        raise SystemExit("bench.py: device init failed: " + L.fftb200_last_error().decode())
+
+    def sync():
+        if dist is not None:
+            import torch
+            torch.cuda.synchronize()
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    n, batch = args.n, args.batch
+    total = n * batch
+    m_in, m_out = L.fft_gpu_alloc(total), L.fft_gpu_alloc(total)
+    plan = L.fft_gpu_plan_1d(n, batch, F.FFT_FORWARD)
+    if not m_in or not m_out or not plan:
+        raise SystemExit("bench.py: setup failed: " + L.fftb200_last_error().decode())
+    din, dout, eng = L.fftb200_devptr_of(m_in), L.fftb200_devptr_of(m_out), L.fftb200_engine_of(plan)
+    # rank r owns transforms [r*batch, (r+1)*batch) of the global job: same stream, different slice
+    L.fftb200_fill_splitmix(din, 43, rank * total, total)
+    launches_per_step = L.fftb200_plan_launches(eng)
+    desc = L.fftb200_plan_describe(eng).decode()
+
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    time_plan(L, eng, din, dout, 1, args.warmup, sync)
+    if sampler:
+        sampler.start()
+    ms = time_plan(L, eng, din, dout, args.steps, 0, sync)
+    # keep the device loaded for long enough that the sampler sees clocks under load
+    if sampler:
+        t_end = time.time() + 0.4
+        while time.time() < t_end:
+            L.fftb200_plan_exec(eng, din, dout)
+        clocks = sampler.stop()
+    ms_max = ms
+    if dist is not None:
+        import torch
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_max = float(t.item())
+
+    # ---- e2e: host buffers through the public host-pointer entry point ----
+    e2e = None
+    if not args.no_e2e:
+        hin, hout = L.fft_alloc_complex(total), L.fft_alloc_complex(total)
+        if hin and hout:
+            L.fftb200_memcpy_d2h(hin, din, total * 16)  # same synthetic data, now host-resident
+            if L.fft_gpu_dft_1d_batch(hin, hout, n, batch, F.FFT_FORWARD) != 0:  # warm-up (also builds the plan cache)
+                raise SystemExit("bench.py: e2e failed: " + L.fftb200_last_error().decode())
+            sync()
+            t0 = time.perf_counter()
+            for _ in range(args.e2e_steps):
+                L.fft_gpu_dft_1d_batch(hin, hout, n, batch, F.FFT_FORWARD)
+            dt = (time.perf_counter() - t0) / args.e2e_steps
+            sync()
+            if dist is not None:
+                import torch
+                t = torch.tensor([dt], dtype=torch.float64, device="cuda")
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                dt = float(t.item())
+            e2e = {"value": flops(n, batch) * world / dt * 1e-9, "unit": "GFLOP/s", "ms_per_step": dt * 1e3,
+                   "h2d_bytes_per_step": total * 16, "d2h_bytes_per_step": total * 16,
+                   "api": "fft_gpu_dft_1d_batch(in, out, n, batch, FFT_FORWARD) on fft_alloc_complex buffers"}
+        L.fft_free(hin)
+        L.fft_free(hout)
+
+    L.fft_gpu_destroy_plan(plan)
+    L.fft_gpu_free(m_in)
+    L.fft_gpu_free(m_out)
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+    peak, peak_src = hbm_peak()
+    alg_bytes = 32.0 * total
+    achieved = alg_bytes / (ms / launches_per_step * 1e-3) * 1e-9 if launches_per_step == 1 else alg_bytes / (ms * 1e-3) * 1e-9
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("n%d_b%d" % (n, batch))
+    except Exception:
+        pass
+    line = {
+        "metric": "batched c2c double FFT GFLOP/s (5*N*log2N*batch/t)", "value": flops(n, batch) * world / (ms_max * 1e-3) * 1e-9,
+        "unit": "GFLOP/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_max,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic (splitmix64 stream, seed 43, generated on the device)",
+        "config": {"workload": "batched c2c double FFT N=%d x %d batch per GPU (BASELINE configs[1])" % (n, batch),
+                   "n": n, "batch_per_gpu": batch, "direction": "forward", "plan": desc,
+                   "l2": "input 32x larger than L2 (4 GiB vs 126 MB): no flush between iterations",
+                   "parallelism": "batch sharded over %d GPU(s), no collective" % world},
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": traffic, "peak_source": peak_src,
+                     "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": ms / launches_per_step},
+        "clocks": clocks, "gpu_launches": launches_per_step * args.steps,
+    }
+    if e2e:
+        line["e2e"] = e2e
+    if world == 1 and not args.no_cpu:
+        try:
+            gf, t, kind, cores, cdesc = cpu_reference(n, args.cpu_sample, 10, 1)
+            line["cpu_baseline"] = {"value": gf, "unit": "GFLOP/s", "cores": cores, "kind": kind, "sample": cdesc}
+        except Exception as e:  # the baseline is reported, never required for the product path
+            line["cpu_baseline"] = {"value": None, "unit": "GFLOP/s", "cores": os.cpu_count(), "kind": "unavailable", "sample": str(e)}
+    print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main_sweep(args):
+    import fftb200_loader
+    F = fftb200_loader.load()
+    L = F.lib
+    F.require_gpu()
+    peak, _ = hbm_peak()
+    for lg in list(range(6, 25)):
+        n = 1 << lg
+        batch = max(1, (1 << 28) >> lg)
+        total = n * batch
+        m_in, m_out = L.fft_gpu_alloc(total), L.fft_gpu_alloc(total)
+        plan = L.fft_gpu_plan_1d(n, batch, -1)
+        din, dout, eng = L.fftb200_devptr_of(m_in), L.fftb200_devptr_of(m_out), L.fftb200_engine_of(plan)
+        L.fftb200_fill_splitmix(din, 43, 0, total)
+        ms = time_plan(L, eng, din, dout, args.steps, args.warmup)
+        print(json.dumps({"n": n, "batch": batch, "ms": ms, "gflops": flops(n, batch) / ms * 1e-6,
+                          "strict_GBps": 32.0 * total / ms * 1e-6, "frac_of_peak": 32.0 * total / ms * 1e-6 / peak,
+                          "plan": L.fftb200_plan_describe(eng).decode()}), flush=True)
+        L.fft_gpu_destroy_plan(plan)
+        L.fft_gpu_free(m_in)
+        L.fft_gpu_free(m_out)
+
+
+if __name__ == "__main__":
+    a = parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if a.impl == "reference":
+        main_reference(a, rank, world)
+    elif a.sweep:
+        main_sweep(a)
+    else:
+        main_b200(a, rank, world, local_rank)

@@ -96,6 +96,8 @@ _SIGS = {
     "fftb200_devptr_of": (_vp, [_vp]),
     "fftb200_host_twiddles": (_vp, [C.c_int]),
     "fftb200_host_chirp": (None, [_vp, C.c_int, C.c_int]),
+    "fftb200_host_tables_release": (None, []),
+    "fftb200_shard_range": (C.c_int, [C.c_longlong, C.c_int, C.c_int, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]),
 }
 EXPORTS = sorted(_SIGS)
 for _name, (_res, _args) in _SIGS.items():
@@ -173,3 +175,11 @@ def host_chirp(n, direction=-1):
     c = np.empty(n, dtype=np.complex128)
     lib.fftb200_host_chirp(ptr(c), n, direction)
     return c
+
+
+def shard_range(batch, world, rank):
+    """(first, count) of the contiguous batch range owned by `rank` (fftb200_shard_range)."""
+    first, count = C.c_longlong(), C.c_longlong()
+    if lib.fftb200_shard_range(batch, world, rank, C.byref(first), C.byref(count)) != 0:
+        raise ValueError("bad shard arguments")
+    return first.value, count.value

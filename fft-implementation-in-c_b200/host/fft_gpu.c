@@ -10,6 +10,7 @@
  */
 #include "../../include/fft_gpu.h"
 #include "../../include/fftb200.h"
+#include "../../include/fftb200_ext.h"
 #include "ref_twiddle.h"
 
 struct fft_gpu_memory {
@@ -170,3 +171,11 @@ int fft_gpu_set_device(int device) {
 /* engine handle of a public plan, for the additive helpers in fftb200_ext.h (timing, async) */
 fftb200_plan* fftb200_engine_of(fft_gpu_plan_t plan) { return plan ? plan->engine : NULL; }
 void* fftb200_devptr_of(fft_gpu_memory_t mem) { return mem ? mem->dptr : NULL; }
+
+int fftb200_shard_range(long long batch, int world, int rank, long long* first, long long* count) {
+    if (batch < 0 || world <= 0 || rank < 0 || rank >= world || !first || !count) return -1;
+    const long long base = batch / world, extra = batch % world;
+    *first = base * rank + (rank < extra ? rank : extra);
+    *count = base + (rank < extra ? 1 : 0);
+    return 0;
+}

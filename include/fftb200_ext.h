@@ -1,0 +1,31 @@
+/*
+ * fftb200_ext.h - additive helpers of the host library (not in the reference's headers; nothing in
+ * fft_auto.h / fft_gpu.h changes because of them).
+ *
+ *  - access to the engine plan / device pointer behind the public opaque handles, so a caller can time
+ *    with CUDA events on the plan's stream or enqueue asynchronously (include/fftb200.h);
+ *  - the batch partition used when a batched job is spread over several GPUs, one process (or one
+ *    fft_gpu_set_device + plan) per GPU: transforms are independent, so rank r of `world` simply owns a
+ *    contiguous range of the batch and there is no exchange step (reference layout: transform b at
+ *    [b*n, (b+1)*n), gpu/fft_cuda.cu:152-156);
+ *  - the host-side table generators (the reference's twiddle recurrence, algorithms/core/radix2_dit.c:
+ *    93,109, and Bluestein chirp, algorithms/core/bluestein.c:59-62) for inspection and tests.
+ */
+#ifndef FFTB200_EXT_H
+#define FFTB200_EXT_H
+
+#include "fft_gpu.h"
+#include "fftb200.h"
+
+fftb200_plan* fftb200_engine_of(fft_gpu_plan_t plan);
+void* fftb200_devptr_of(fft_gpu_memory_t mem);
+
+/* Contiguous partition of `batch` transforms over `world` ranks: the first (batch % world) ranks own one
+ * transform more. Returns 0, or -1 on bad arguments. count may be 0 when world > batch. */
+int fftb200_shard_range(long long batch, int world, int rank, long long* first, long long* count);
+
+const double* fftb200_host_twiddles(int n);           /* n - 1 complex, stage s entry j at 2^(s-1) - 1 + j */
+void fftb200_host_chirp(double* out, int n, int dir); /* n complex */
+void fftb200_host_tables_release(void);
+
+#endif /* FFTB200_EXT_H */

@@ -143,6 +143,13 @@ class Par:
         for name in ("oracle_ref_four_step", "oracle_ref_radix2_parallel"):
             getattr(L, name).argtypes = [_dp, C.c_int, C.c_int, C.c_int]
             getattr(L, name).restype = None
+        L.oracle_ref_batch_execute.argtypes = [_dp, _dp, C.c_int, C.c_long, C.c_int, C.c_int]
+
+    def batch_execute(self, x, out, sign, threads):
+        """Reference fft_plan_dft_1d / fft_execute_dft over a (batch, n) array, one plan per thread."""
+        batch, n = x.shape
+        return self.lib.oracle_ref_batch_execute(_ptr(x.view(np.float64)), _ptr(out.view(np.float64)), n, batch,
+                                                 sign, threads)
 
     def radix2_parallel(self, x, direction, threads):
         self.lib.oracle_ref_radix2_parallel(_ptr(x.view(np.float64)), x.size, direction, threads)
