@@ -31,4 +31,9 @@ const KernelInfo* kernels_contig(int* count);
 const KernelInfo* kernels_strided(int* count);
 const KernelInfo* kernels_last(int* count);
 
+// persistent TMA-fed kernels (fft_pipe.cuh), defined in fft_kernels_pipe.cu
+struct PipeArgs;
+const void* pipe_func(int logn);                                               // nullptr if no variant
+void launch_pipe(int logn, const PipeArgs& a, int grid, cudaStream_t s);
+
 }  // namespace fftb200

@@ -1,0 +1,228 @@
+// fft_pipe.cuh - the persistent, TMA-fed Stockham kernel for whole transforms of 512 .. 4096 points.
+//
+// This is the kernel behind BASELINE config 2 (N = 4096 x 65536 batch). It replaces the same reference
+// code as fft_tile.cuh (the butterfly loop of algorithms/core/radix2_dit.c:70-119 and the never-built
+// cufftExecZ2Z call of gpu/fft_cuda.cu:166-185) for the sizes where one transform fits a 64 KB tile.
+//
+// Structure (one CTA per SM, 512 threads = two groups of 256):
+//   * a tile is 4096 consecutive complex doubles of the batch buffer = 4096/N whole transforms;
+//   * three 64 KB shared-memory buffers form a ring. One thread issues a 1-D bulk async copy (TMA,
+//     cp.async.bulk + mbarrier complete_tx) for tile k+3 as soon as tile k has left its buffer, so two
+//     tiles (128 KB) are always in flight per SM while a third is being computed: HBM never waits for
+//     the FP64 pipe and the other way round;
+//   * the two thread groups work on alternate tiles and meet only through the ring, so one group's
+//     shared-memory exchange overlaps the other group's butterflies;
+//   * a thread holds 16 points in registers. Three sub-passes (radix N/256, 16, 16) regroup the
+//     reference's log2 N radix-2 DIT stages; between sub-passes the tile is exchanged IN PLACE in the
+//     buffer the TMA filled, with an XOR swizzle (element ^ ((element >> 4) & 7)) that makes every
+//     128-bit shared-memory access pattern conflict-free without padding;
+//   * results leave from registers with 128-bit stores, 512 contiguous bytes per warp instruction.
+//
+// Twiddles: all stages handled here have m <= 4096, where the reference's recurrence
+// (radix2_dit.c:93,109) is still within 3e-14 (relative L2 of the whole transform) of correctly rounded
+// twiddles - SURVEY.md 7.0 "hybrid". The kernel therefore reads the ACCURATE per-stage table (same layout
+// as the reference-recurrence table), which has the symmetry w[q + m/4] = -i * w[q]; only 8 of the 15
+// twiddles of a radix-16 butterfly are loaded, the other 7 are free sign/swap variants. The last
+// sub-pass's 8 twiddles depend only on the thread index and stay in registers for the whole kernel.
+#pragma once
+#include "fft_tile.cuh"
+
+namespace fftb200 {
+
+struct PipeArgs {
+    const cd* in;
+    cd* out;
+    const cd* tab;     // accurate per-stage twiddle table (stage s, j) at 2^(s-1) - 1 + j
+    long long ntiles;  // ceil(batch / (4096 / N))
+    long long batch;
+    int inverse;
+    double scale;      // 1/N, applied when inverse
+};
+
+constexpr int PIPE_TILE = 4096;              // complex elements per tile
+constexpr int PIPE_STAGES = 3;               // ring depth
+constexpr int PIPE_GROUP = 256;              // threads per group
+constexpr size_t PIPE_SMEM = (size_t)PIPE_STAGES * PIPE_TILE * sizeof(cd) + 64;
+
+__device__ __forceinline__ int pipe_swz(int idx) { return idx ^ ((idx >> 4) & 7); }
+
+// (lo, hi) <- (lo + (-i*w)*hi, lo - (-i*w)*hi): the q + m/4 twiddle of an accurate table
+__device__ __forceinline__ void bfly_mi(cd& lo, cd& hi, const cd w) {
+    double sx = fma(w.y, hi.x, lo.x);
+    double sy = fma(w.y, hi.y, lo.y);
+    sx = fma(w.x, hi.y, sx);
+    sy = fma(-w.x, hi.x, sy);
+    hi.x = fma(2.0, lo.x, -sx);
+    hi.y = fma(2.0, lo.y, -sy);
+    lo.x = sx;
+    lo.y = sy;
+}
+
+// radix-2^LR DIT over w[] (bit-reversed placement) with the 2^(LR-1) stored twiddles tw[h],
+// h = 2^(s-1) + q for q < max(1, 2^(s-2)); positions q >= 2^(s-2) use -i * tw[h - 2^(s-2)].
+template <int LR, int S, int BASE, int Q>
+struct SubStageSym {
+    static __device__ __forceinline__ void run(cd* w, const cd* tw) {
+        constexpr int HH = 1 << (S - 1), R = 1 << LR;
+        if constexpr (S >= 2 && 2 * Q >= HH) bfly_mi(w[BASE + Q], w[BASE + Q + HH], tw[HH + Q - HH / 2]);
+        else bfly(w[BASE + Q], w[BASE + Q + HH], tw[HH + Q]);
+        if constexpr (Q + 1 < HH) SubStageSym<LR, S, BASE, Q + 1>::run(w, tw);
+        else if constexpr (BASE + 2 * HH < R) SubStageSym<LR, S, BASE + 2 * HH, 0>::run(w, tw);
+        else if constexpr (S < LR) SubStageSym<LR, S + 1, 0, 0>::run(w, tw);
+    }
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// 1-D bulk async copy global -> shared, completion counted in bytes on `bar`
+__device__ __forceinline__ void bulk_load(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void group_sync(int g) {
+    asm volatile("bar.sync %0, %1;" ::"r"(g + 1), "r"(PIPE_GROUP) : "memory");
+}
+
+template <int LOGN>
+__global__ void __launch_bounds__(2 * PIPE_GROUP, 1) fft_pipe_kernel(const PipeArgs a) {
+    static_assert(LOGN >= 9 && LOGN <= 12, "one transform must be 512 .. 4096 points");
+    constexpr int N = 1 << LOGN, NT = PIPE_TILE / N;  // transforms per tile
+    constexpr int LR0 = LOGN - 8, R0 = 1 << LR0, NB0 = 16 / R0;
+    constexpr int LN16 = LOGN - 4;                    // log2 (N / 16)
+
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    cd* const bufs = reinterpret_cast<cd*>(smem_raw);
+    uint64_t* const full = reinterpret_cast<uint64_t*>(smem_raw + (size_t)PIPE_STAGES * PIPE_TILE * sizeof(cd));
+
+    const int g = threadIdx.x / PIPE_GROUP, t = threadIdx.x % PIPE_GROUP;
+    const long long first = blockIdx.x, stride = gridDim.x;
+    const long long my_tiles = first < a.ntiles ? (a.ntiles - first + stride - 1) / stride : 0;
+
+    auto issue = [&](long long k, int b) {  // one thread: start the load of this CTA's k-th tile into buffer b
+        const long long tile = first + k * stride;
+        long long nvalid = a.batch - tile * NT;
+        if (nvalid > NT) nvalid = NT;
+        const uint32_t bytes = (uint32_t)nvalid * N * (uint32_t)sizeof(cd);
+        mbar_expect_tx(&full[b], bytes);
+        bulk_load(bufs + (size_t)b * PIPE_TILE, a.in + tile * PIPE_TILE, bytes, &full[b]);
+    };
+
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int b = 0; b < PIPE_STAGES; b++) mbar_init(&full[b], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int k = 0; k < PIPE_STAGES && k < my_tiles; k++) issue(k, k);
+    }
+
+    // thread-constant butterfly coordinates of the two radix-16 sub-passes
+    const int j = t >> LN16;              // transform within the tile
+    const int v = t & ((1 << LN16) - 1);  // butterfly within the transform
+    const int cp = v & 15, kloc1 = v >> 4;
+    const cd* const tab = a.tab;
+    // sub-pass 2 twiddles: stage (LN16 + s), position kappa = v  ->  tab[(h << LN16) + v - 1]
+    cd w2[16];
+    {
+        const cd* tp = tab + (v - 1);
+#pragma unroll
+        for (int s = 1; s <= 4; s++) {
+            const int hh = 1 << (s - 1);
+#pragma unroll
+            for (int q = 0; q < (s >= 2 ? hh / 2 : 1); q++) w2[hh + q] = __ldg(tp + ((long long)(hh + q) << LN16));
+        }
+    }
+    const cd* const tp1 = tab + (kloc1 - 1);
+    const bool inv = a.inverse != 0;
+    const double sc = inv ? a.scale : 1.0;
+
+    int b = g % PIPE_STAGES;   // ring slot of tile k
+    uint32_t round = 0;        // k / PIPE_STAGES
+    for (long long k = g; k < my_tiles; k += 2) {
+        cd* const sm = bufs + (size_t)b * PIPE_TILE;
+        mbar_wait(&full[b], round & 1);
+        cd x[16];
+        // ---- sub-pass 0: radix R0, exact constants, in place (each thread owns idx = t + 256 e) ----
+#pragma unroll
+        for (int e = 0; e < 16; e++) {
+            cd y = sm[t + 256 * e];
+            if (inv) y.y = -y.y;
+            x[(e / R0) * R0 + bitrev_c<LR0>(e % R0)] = y;
+        }
+#pragma unroll
+        for (int bb = 0; bb < NB0; bb++) SubStageExact<LR0, 1, 0, 0>::run(&x[bb * R0]);
+        __syncwarp();  // the swizzle moves a thread's slots within its warp's 32-element rows
+#pragma unroll
+        for (int e = 0; e < 16; e++) sm[pipe_swz(t + 256 * e)] = x[e];
+        group_sync(g);
+        // ---- sub-pass 1: radix 16, M = R0, S = 16 ----
+        {
+            const int base = j * N + cp + 256 * kloc1;
+            cd y[16];
+#pragma unroll
+            for (int rho = 0; rho < 16; rho++) y[bitrev_c<4>(rho)] = sm[pipe_swz(base + 16 * rho)];
+            cd tw[16];
+#pragma unroll
+            for (int s = 1; s <= 4; s++) {
+                const int hh = 1 << (s - 1);
+#pragma unroll
+                for (int q = 0; q < (s >= 2 ? hh / 2 : 1); q++) tw[hh + q] = __ldg(tp1 + ((hh + q) << LR0));
+            }
+            SubStageSym<4, 1, 0, 0>::run(y, tw);
+            group_sync(g);  // every gather of this sub-pass is done
+#pragma unroll
+            for (int q = 0; q < 16; q++) sm[pipe_swz(j * N + v + (q << LN16))] = y[q];
+        }
+        group_sync(g);
+        // ---- sub-pass 2: radix 16, M = N/16, S = 1 ----
+        {
+            const int base = j * N + 16 * v;
+#pragma unroll
+            for (int rho = 0; rho < 16; rho++) x[bitrev_c<4>(rho)] = sm[pipe_swz(base + rho)];
+        }
+        group_sync(g);  // the buffer is free: refill it with this CTA's tile k + 3
+        if (t == 0 && k + PIPE_STAGES < my_tiles) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            issue(k + PIPE_STAGES, b);
+        }
+        SubStageSym<4, 1, 0, 0>::run(x, w2);
+        {
+            const long long tile = first + k * stride;
+            const bool valid = tile * NT + j < a.batch;
+            cd* p = a.out + tile * PIPE_TILE + j * N + v;
+            if (valid) {
+#pragma unroll
+                for (int q = 0; q < 16; q++) {
+                    cd r = x[q];
+                    if (inv) { r.x *= sc; r.y *= -sc; }
+                    p[q << LN16] = r;
+                }
+            }
+        }
+        // the other group consumed the next ring slot; this group's next tile is two slots ahead
+        b += 2;
+        if (b >= PIPE_STAGES) { b -= PIPE_STAGES; round++; }
+    }
+}
+
+}  // namespace fftb200

@@ -18,6 +18,7 @@
 #include "../../include/fftb200.h"
 #include "fft_aux.cuh"
 #include "fft_catalog.h"
+#include "fft_pipe.cuh"
 
 using namespace fftb200;
 
@@ -51,6 +52,7 @@ struct DeviceState {
     cd* tab = nullptr;   // largest twiddle table uploaded so far (older, smaller ones stay alive in `old`)
     int tab_n = 0;
     std::vector<cd*> old;
+    cd* acc = nullptr;   // accurate (correctly rounded) stage tables, fixed size ACC_N
     char name[256] = "";
 };
 static DeviceState g_dev[64];
@@ -104,6 +106,8 @@ extern "C" int fftb200_device_reset(void) {
     if (cur_device(&s) != 0) return -1;
     CU(cudaDeviceSynchronize());
     if (s->tab) cudaFree(s->tab);
+    if (s->acc) cudaFree(s->acc);
+    s->acc = nullptr;
     for (cd* p : s->old) cudaFree(p);
     s->old.clear();
     s->tab = nullptr;
@@ -168,8 +172,11 @@ extern "C" int fftb200_pointwise_mul(void* y, const void* a, const void* b, size
 // ---------------------------------------------------------------------------------------------
 enum { BUF_IN = 0, BUF_OUT = 1, BUF_SCRATCH = 2 };
 
+enum { ACC_N = 8192 };  // accurate tables cover stages m <= 8192 (hybrid twiddles)
+
 struct Pass {
-    const KernelInfo* k;
+    const KernelInfo* k;   // nullptr: persistent TMA kernel fft_pipe_kernel<log_p>
+    int log_p;
     int log_m;
     long long ntiles;
     int src, dst;
@@ -184,6 +191,7 @@ struct fftb200_plan {
     int m = 0;                 // power-of-two length (== n for C2C / R2C)
     std::vector<Pass> passes;  // forward or inverse c2c of length m over `batch`
     const cd* tab = nullptr;
+    const cd* acc = nullptr;   // accurate tables (nullptr: reference-recurrence tables everywhere)
     cd* scratch = nullptr;     // ping-pong buffer for multi-pass plans
     cd* work = nullptr;        // Bluestein / R2C: padded complex work array, m * batch
     cd* chirp = nullptr;       // Bluestein: n entries
@@ -235,9 +243,25 @@ static int build_passes(fftb200_plan* p, DeviceState* ds) {
     const int np = (int)sizes.size();
     int log_m = 0;
     const int persistent = getenv("FFTB200_PERSISTENT") ? atoi(getenv("FFTB200_PERSISTENT")) : 1;
+    if (np == 1 && L >= 9 && L <= 12 && p->acc && !getenv("FFTB200_NO_PIPE")) {
+        Pass ps;
+        ps.k = nullptr; ps.log_p = L; ps.log_m = 0;
+        const int nt = PIPE_TILE >> L;
+        ps.ntiles = ((long long)p->batch + nt - 1) / nt;
+        ps.src = BUF_IN; ps.dst = BUF_OUT; ps.final_pass = 1;
+        CU(cudaFuncSetAttribute(pipe_func(L), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PIPE_SMEM));
+        long long g = ds->sms < ps.ntiles ? ds->sms : ps.ntiles;
+        ps.grid = (int)(g < 1 ? 1 : g);
+        p->passes.push_back(ps);
+        char b[64];
+        snprintf(b, sizeof(b), "P%d(tma ring %d x 64KB, 2x256 thr)", L, PIPE_STAGES);
+        p->desc += b;
+        return 0;
+    }
     for (int i = 0; i < np; i++) {
         Pass ps;
         const int lp = sizes[i];
+        ps.log_p = lp;
         int mode;
         if (np == 1) mode = MODE_CONTIG;
         else if (i == np - 1) mode = MODE_LAST;
@@ -284,6 +308,14 @@ static int build_passes(fftb200_plan* p, DeviceState* ds) {
 // Enqueue the power-of-two c2c passes: `inverse` selects conjugated twiddles and the 1/m scale.
 static int enqueue_c2c(fftb200_plan* p, const cd* in, cd* out, int inverse) {
     for (const Pass& ps : p->passes) {
+        if (!ps.k) {
+            PipeArgs pa;
+            pa.in = in; pa.out = out; pa.tab = p->acc;
+            pa.ntiles = ps.ntiles; pa.batch = p->batch;
+            pa.inverse = inverse; pa.scale = 1.0 / (double)p->m;
+            launch_pipe(ps.log_p, pa, ps.grid, p->stream);
+            continue;
+        }
         TileArgs a;
         const cd* src = ps.src == BUF_IN ? in : ps.src == BUF_OUT ? out : p->scratch;
         cd* dst = ps.dst == BUF_OUT ? out : p->scratch;
@@ -311,6 +343,23 @@ static int upload_table(fftb200_plan* p, DeviceState* ds, const fftb200_plan_des
     ds->tab = t;
     ds->tab_n = d->table_n;
     p->tab = t;
+    return 0;
+}
+
+static int upload_accurate(fftb200_plan* p, DeviceState* ds, const fftb200_plan_desc* d) {
+    p->acc = nullptr;
+    if (!d->twiddles_accurate || d->accurate_n < 2) return 0;
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (!ds->acc) {
+        if (d->accurate_n != ACC_N) return fail("accurate twiddle table must cover n = %d", (int)ACC_N);
+        cd* t = nullptr;
+        const size_t bytes = sizeof(cd) * (size_t)(ACC_N - 1);
+        CU(cudaMalloc(&t, bytes));
+        CU(cudaMemcpy(t, d->twiddles_accurate, bytes, cudaMemcpyHostToDevice));
+        CU(cudaStreamSynchronize(cudaStreamLegacy));
+        ds->acc = t;
+    }
+    p->acc = ds->acc;
     return 0;
 }
 
@@ -342,6 +391,7 @@ extern "C" int fftb200_plan_create(fftb200_plan** out, const fftb200_plan_desc* 
         if (cudaStreamCreateWithFlags(&p->stream2, cudaStreamNonBlocking) != cudaSuccess) { rc = fail("cudaStreamCreate failed"); break; }
         if (cudaEventCreate(&p->ev0) != cudaSuccess || cudaEventCreate(&p->ev1) != cudaSuccess) { rc = fail("cudaEventCreate failed"); break; }
         if ((rc = upload_table(p, ds, d, p->m)) != 0) break;
+        if ((rc = upload_accurate(p, ds, d)) != 0) break;
         char head[96];
         snprintf(head, sizeof(head), "%s n=%d b=%d dir=%d: ", d->kind == FFTB200_C2C ? "c2c" : d->kind == FFTB200_R2C ? "r2c" : "bluestein", d->n, d->batch, d->direction);
         p->desc = head;

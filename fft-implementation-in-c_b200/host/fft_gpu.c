@@ -98,6 +98,7 @@ fftb200_plan* fftb200_host_make_plan(int n, int batch, int direction, int kind) 
         d.table_n = n;
     }
     d.twiddles = fftb200_host_twiddles(d.table_n);
+    d.twiddles_accurate = fftb200_host_twiddles_accurate(&d.accurate_n);
     fftb200_plan* p = NULL;
     if (!d.twiddles || fftb200_plan_create(&p, &d) != 0) { report("plan"); p = NULL; }
     free(chirp);

@@ -78,6 +78,42 @@ static void fill_stage(double* t, int s) {
     }
 }
 
+#define ACC_N 8192
+static double* g_acc = NULL;
+
+const double* fftb200_host_twiddles_accurate(int* n_out) {
+    const char* e = getenv("FFTB200_TWIDDLE");
+    if (e && strcmp(e, "ref") == 0) return NULL;
+    pthread_mutex_lock(&g_mu);
+    if (!g_acc) {
+        double* t = (double*)malloc(sizeof(double) * 2 * (ACC_N - 1));
+        if (t) {
+            for (int s = 1; (1 << s) <= ACC_N; s++) {
+                const int half = 1 << (s - 1);
+                double* ts = t + 2 * ((size_t)half - 1);
+                for (int j = 0; j < half; j++) {
+                    /* exact quarter-turn symmetry by construction: entry j + half/2 = -i * entry j */
+                    if (s >= 2 && j >= half / 2) {
+                        ts[2 * j] = ts[2 * (j - half / 2) + 1];
+                        ts[2 * j + 1] = -ts[2 * (j - half / 2)];
+                        continue;
+                    }
+                    long double a = -2.0L * 3.14159265358979323846264338327950288L * (long double)j / (long double)(2 * half);
+                    ts[2 * j] = (double)cosl(a);
+                    ts[2 * j + 1] = (double)sinl(a);
+                }
+            }
+            t[0] = 1.0; t[1] = 0.0;                 /* stage 1: w = 1 */
+            if (ACC_N >= 4) { t[2] = 1.0; t[3] = 0.0; t[4] = 0.0; t[5] = -1.0; } /* stage 2: 1, -i exactly */
+            g_acc = t;
+        }
+    }
+    const double* r = g_acc;
+    pthread_mutex_unlock(&g_mu);
+    if (n_out) *n_out = ACC_N;
+    return r;
+}
+
 const double* fftb200_host_twiddles(int n) {
     if (n < 1 || (n & (n - 1))) return NULL;
     pthread_mutex_lock(&g_mu);
@@ -106,6 +142,8 @@ void fftb200_host_tables_release(void) {
     for (int i = 0; i < g_nold; i++) free(g_old[i]);
     g_nold = 0;
     free(g_tab);
+    free(g_acc);
+    g_acc = NULL;
     g_tab = NULL;
     g_n = 0;
     pthread_mutex_unlock(&g_mu);

@@ -42,6 +42,10 @@ typedef struct fftb200_plan_desc {
                             /* entry (stage s, j) at 2^(s-1) - 1 + j. table_n = n, or Bluestein's m      */
     int table_n;
     const double* chirp;    /* HOST, n complex, Bluestein only: chirp for `direction`                    */
+    const double* twiddles_accurate; /* HOST, optional: correctly rounded stage tables, same layout, for  */
+    int accurate_n;                  /* size accurate_n (must be 8192). When given, stages with m <= 4096 */
+                                     /* of single-pass plans use them (3e-14 from the reference, see      */
+                                     /* fft_pipe.cuh); NULL keeps the reference recurrence everywhere.    */
     unsigned flags;         /* reserved                                                                  */
 } fftb200_plan_desc;
 
