@@ -33,7 +33,7 @@ const KernelInfo* kernels_last(int* count);
 
 // persistent TMA-fed kernels (fft_pipe.cuh), defined in fft_kernels_pipe.cu
 struct PipeArgs;
-const void* pipe_func(int logn);                                               // nullptr if no variant
+const void* pipe_func(int logn, int inverse);                                  // nullptr if no variant
 void launch_pipe(int logn, const PipeArgs& a, int grid, cudaStream_t s);
 
 }  // namespace fftb200

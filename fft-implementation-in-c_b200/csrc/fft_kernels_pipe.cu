@@ -3,27 +3,27 @@
 #include "fft_pipe.cuh"
 namespace fftb200 {
 
-template <int LOGN>
+template <int LOGN, bool INV>
 static void launch_pipe_t(const PipeArgs& a, int grid, cudaStream_t s) {
-    fft_pipe_kernel<LOGN><<<grid, 2 * PIPE_GROUP, PIPE_SMEM, s>>>(a);
+    fft_pipe_kernel<LOGN, INV><<<grid, 2 * PIPE_GROUP, PIPE_SMEM, s>>>(a);
 }
 
-const void* pipe_func(int logn) {
+#define PIPE_CASES(X) X(9) X(10) X(11) X(12)
+
+const void* pipe_func(int logn, int inverse) {
     switch (logn) {
-        case 9: return (const void*)fft_pipe_kernel<9>;
-        case 10: return (const void*)fft_pipe_kernel<10>;
-        case 11: return (const void*)fft_pipe_kernel<11>;
-        case 12: return (const void*)fft_pipe_kernel<12>;
+#define X(L) case L: return inverse ? (const void*)fft_pipe_kernel<L, true> : (const void*)fft_pipe_kernel<L, false>;
+        PIPE_CASES(X)
+#undef X
     }
     return nullptr;
 }
 
 void launch_pipe(int logn, const PipeArgs& a, int grid, cudaStream_t s) {
     switch (logn) {
-        case 9: launch_pipe_t<9>(a, grid, s); break;
-        case 10: launch_pipe_t<10>(a, grid, s); break;
-        case 11: launch_pipe_t<11>(a, grid, s); break;
-        case 12: launch_pipe_t<12>(a, grid, s); break;
+#define X(L) case L: if (a.inverse) launch_pipe_t<L, true>(a, grid, s); else launch_pipe_t<L, false>(a, grid, s); break;
+        PIPE_CASES(X)
+#undef X
     }
 }
 }  // namespace fftb200

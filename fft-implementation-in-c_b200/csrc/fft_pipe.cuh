@@ -42,7 +42,8 @@ struct PipeArgs {
 constexpr int PIPE_TILE = 4096;              // complex elements per tile
 constexpr int PIPE_STAGES = 3;               // ring depth
 constexpr int PIPE_GROUP = 256;              // threads per group
-constexpr size_t PIPE_SMEM = (size_t)PIPE_STAGES * PIPE_TILE * sizeof(cd) + 64;
+constexpr int PIPE_TW1 = 16 * 8;             // shared copy of the middle sub-pass twiddles: [kloc][8]
+constexpr size_t PIPE_SMEM = (size_t)PIPE_STAGES * PIPE_TILE * sizeof(cd) + PIPE_TW1 * sizeof(cd) + 64;
 
 __device__ __forceinline__ int pipe_swz(int idx) { return idx ^ ((idx >> 4) & 7); }
 
@@ -101,7 +102,11 @@ __device__ __forceinline__ void group_sync(int g) {
     asm volatile("bar.sync %0, %1;" ::"r"(g + 1), "r"(PIPE_GROUP) : "memory");
 }
 
-template <int LOGN>
+__device__ __forceinline__ cd cmulc(const cd a, const double c, const double d) {  // a * (c + i d)
+    return make_double2(fma(a.x, c, -(a.y * d)), fma(a.x, d, a.y * c));
+}
+
+template <int LOGN, bool INV>
 __global__ void __launch_bounds__(2 * PIPE_GROUP, 1) fft_pipe_kernel(const PipeArgs a) {
     static_assert(LOGN >= 9 && LOGN <= 12, "one transform must be 512 .. 4096 points");
     constexpr int N = 1 << LOGN, NT = PIPE_TILE / N;  // transforms per tile
@@ -110,14 +115,15 @@ __global__ void __launch_bounds__(2 * PIPE_GROUP, 1) fft_pipe_kernel(const PipeA
 
     extern __shared__ __align__(128) unsigned char smem_raw[];
     cd* const bufs = reinterpret_cast<cd*>(smem_raw);
-    uint64_t* const full = reinterpret_cast<uint64_t*>(smem_raw + (size_t)PIPE_STAGES * PIPE_TILE * sizeof(cd));
+    cd* const tw1s = bufs + (size_t)PIPE_STAGES * PIPE_TILE;
+    uint64_t* const full = reinterpret_cast<uint64_t*>(tw1s + PIPE_TW1);
 
     const int g = threadIdx.x / PIPE_GROUP, t = threadIdx.x % PIPE_GROUP;
-    const long long first = blockIdx.x, stride = gridDim.x;
-    const long long my_tiles = first < a.ntiles ? (a.ntiles - first + stride - 1) / stride : 0;
+    const int first = blockIdx.x, stride = gridDim.x;
+    const int my_tiles = first < a.ntiles ? (int)((a.ntiles - first + stride - 1) / stride) : 0;
 
-    auto issue = [&](long long k, int b) {  // one thread: start the load of this CTA's k-th tile into buffer b
-        const long long tile = first + k * stride;
+    auto issue = [&](int k, int b) {  // one thread: start the load of this CTA's k-th tile into buffer b
+        const long long tile = first + (long long)k * stride;
         long long nvalid = a.batch - tile * NT;
         if (nvalid > NT) nvalid = NT;
         const uint32_t bytes = (uint32_t)nvalid * N * (uint32_t)sizeof(cd);
@@ -131,6 +137,13 @@ __global__ void __launch_bounds__(2 * PIPE_GROUP, 1) fft_pipe_kernel(const PipeA
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
+    // middle sub-pass twiddles -> shared: stage (LR0 + s), position kappa = kloc: tab[(h << LR0) + kloc - 1]
+    // for h in {1, 2, 4, 5, 8, 9, 10, 11} (the other 7 positions are -i times one of these)
+    if (threadIdx.x < R0 * 8) {
+        const int kl = threadIdx.x >> 3, e = threadIdx.x & 7;
+        const int h = e == 0 ? 1 : e == 1 ? 2 : e < 4 ? 2 + e : 4 + e;
+        tw1s[threadIdx.x] = __ldg(a.tab + ((h << LR0) + kl - 1));
+    }
     __syncthreads();
     if (threadIdx.x == 0) {
         for (int k = 0; k < PIPE_STAGES && k < my_tiles; k++) issue(k, k);
@@ -140,25 +153,20 @@ __global__ void __launch_bounds__(2 * PIPE_GROUP, 1) fft_pipe_kernel(const PipeA
     const int j = t >> LN16;              // transform within the tile
     const int v = t & ((1 << LN16) - 1);  // butterfly within the transform
     const int cp = v & 15, kloc1 = v >> 4;
-    const cd* const tab = a.tab;
-    // sub-pass 2 twiddles: stage (LN16 + s), position kappa = v  ->  tab[(h << LN16) + v - 1]
-    cd w2[16];
-    {
-        const cd* tp = tab + (v - 1);
-#pragma unroll
-        for (int s = 1; s <= 4; s++) {
-            const int hh = 1 << (s - 1);
-#pragma unroll
-            for (int q = 0; q < (s >= 2 ? hh / 2 : 1); q++) w2[hh + q] = __ldg(tp + ((long long)(hh + q) << LN16));
-        }
-    }
-    const cd* const tp1 = tab + (kloc1 - 1);
-    const bool inv = a.inverse != 0;
-    const double sc = inv ? a.scale : 1.0;
+    // last sub-pass: stage (LN16 + s), position kappa = v -> tab[(h << LN16) + v - 1]. The four powers
+    // w^8, w^4, w^2, w (h = 1, 2, 4, 8) stay in registers; h = 5, 9, 10, 11 are w^2 * W8, w * W16, w * W8,
+    // w * W16^3, rebuilt per tile (16 FP64 instructions) to keep the register file free of spills.
+    const cd wa = __ldg(a.tab + (v - 1) + (1 << LN16)), wb = __ldg(a.tab + (v - 1) + (2 << LN16));
+    const cd wc = __ldg(a.tab + (v - 1) + (4 << LN16)), wd = __ldg(a.tab + (v - 1) + (8 << LN16));
+    const int rd1 = j * N + cp + 256 * kloc1;   // sub-pass 1 gather base
+    const int wr1 = j * N + v;                  // sub-pass 1 scatter base
+    const int rd2 = j * N + 16 * v;             // sub-pass 2 gather base
+    const cd* const tw1p = tw1s + kloc1 * 8;
+    const double sc = a.scale;
 
     int b = g % PIPE_STAGES;   // ring slot of tile k
     uint32_t round = 0;        // k / PIPE_STAGES
-    for (long long k = g; k < my_tiles; k += 2) {
+    for (int k = g; k < my_tiles; k += 2) {
         cd* const sm = bufs + (size_t)b * PIPE_TILE;
         mbar_wait(&full[b], round & 1);
         cd x[16];
@@ -166,7 +174,7 @@ __global__ void __launch_bounds__(2 * PIPE_GROUP, 1) fft_pipe_kernel(const PipeA
 #pragma unroll
         for (int e = 0; e < 16; e++) {
             cd y = sm[t + 256 * e];
-            if (inv) y.y = -y.y;
+            if (INV) y.y = -y.y;
             x[(e / R0) * R0 + bitrev_c<LR0>(e % R0)] = y;
         }
 #pragma unroll
@@ -177,44 +185,45 @@ __global__ void __launch_bounds__(2 * PIPE_GROUP, 1) fft_pipe_kernel(const PipeA
         group_sync(g);
         // ---- sub-pass 1: radix 16, M = R0, S = 16 ----
         {
-            const int base = j * N + cp + 256 * kloc1;
             cd y[16];
 #pragma unroll
-            for (int rho = 0; rho < 16; rho++) y[bitrev_c<4>(rho)] = sm[pipe_swz(base + 16 * rho)];
+            for (int rho = 0; rho < 16; rho++) y[bitrev_c<4>(rho)] = sm[pipe_swz(rd1 + 16 * rho)];
             cd tw[16];
-#pragma unroll
-            for (int s = 1; s <= 4; s++) {
-                const int hh = 1 << (s - 1);
-#pragma unroll
-                for (int q = 0; q < (s >= 2 ? hh / 2 : 1); q++) tw[hh + q] = __ldg(tp1 + ((hh + q) << LR0));
-            }
+            tw[1] = tw1p[0]; tw[2] = tw1p[1]; tw[4] = tw1p[2]; tw[5] = tw1p[3];
+            tw[8] = tw1p[4]; tw[9] = tw1p[5]; tw[10] = tw1p[6]; tw[11] = tw1p[7];
             SubStageSym<4, 1, 0, 0>::run(y, tw);
             group_sync(g);  // every gather of this sub-pass is done
 #pragma unroll
-            for (int q = 0; q < 16; q++) sm[pipe_swz(j * N + v + (q << LN16))] = y[q];
+            for (int q = 0; q < 16; q++) sm[pipe_swz(wr1 + (q << LN16))] = y[q];
         }
         group_sync(g);
         // ---- sub-pass 2: radix 16, M = N/16, S = 1 ----
-        {
-            const int base = j * N + 16 * v;
 #pragma unroll
-            for (int rho = 0; rho < 16; rho++) x[bitrev_c<4>(rho)] = sm[pipe_swz(base + rho)];
-        }
+        for (int rho = 0; rho < 16; rho++) x[bitrev_c<4>(rho)] = sm[pipe_swz(rd2 + rho)];
         group_sync(g);  // the buffer is free: refill it with this CTA's tile k + 3
         if (t == 0 && k + PIPE_STAGES < my_tiles) {
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             issue(k + PIPE_STAGES, b);
         }
-        SubStageSym<4, 1, 0, 0>::run(x, w2);
         {
-            const long long tile = first + k * stride;
+            constexpr double C8 = 0.70710678118654752440, C16 = 0.92387953251128675613, S16 = 0.38268343236508977173;
+            cd tw[16];
+            tw[1] = wa; tw[2] = wb; tw[4] = wc; tw[8] = wd;
+            tw[5] = make_double2((wc.x + wc.y) * C8, (wc.y - wc.x) * C8);  // w^2 * (1 - i)/sqrt2
+            tw[9] = cmulc(wd, C16, -S16);
+            tw[10] = make_double2((wd.x + wd.y) * C8, (wd.y - wd.x) * C8);
+            tw[11] = cmulc(wd, S16, -C16);
+            SubStageSym<4, 1, 0, 0>::run(x, tw);
+        }
+        {
+            const long long tile = first + (long long)k * stride;
             const bool valid = tile * NT + j < a.batch;
-            cd* p = a.out + tile * PIPE_TILE + j * N + v;
+            cd* p = a.out + tile * PIPE_TILE + wr1;
             if (valid) {
 #pragma unroll
                 for (int q = 0; q < 16; q++) {
                     cd r = x[q];
-                    if (inv) { r.x *= sc; r.y *= -sc; }
+                    if (INV) { r.x *= sc; r.y *= -sc; }
                     p[q << LN16] = r;
                 }
             }

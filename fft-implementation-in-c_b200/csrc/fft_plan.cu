@@ -249,7 +249,8 @@ static int build_passes(fftb200_plan* p, DeviceState* ds) {
         const int nt = PIPE_TILE >> L;
         ps.ntiles = ((long long)p->batch + nt - 1) / nt;
         ps.src = BUF_IN; ps.dst = BUF_OUT; ps.final_pass = 1;
-        CU(cudaFuncSetAttribute(pipe_func(L), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PIPE_SMEM));
+        for (int iv = 0; iv < 2; iv++)
+            CU(cudaFuncSetAttribute(pipe_func(L, iv), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PIPE_SMEM));
         long long g = ds->sms < ps.ntiles ? ds->sms : ps.ntiles;
         ps.grid = (int)(g < 1 ? 1 : g);
         p->passes.push_back(ps);
