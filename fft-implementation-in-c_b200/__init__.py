@@ -11,7 +11,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libfft_b200.so")
+LIB_PATH = os.environ.get("FFTB200_LIB") or os.path.join(_HERE, "lib", "libfft_b200.so")  # env: A/B builds
 
 FFT_FORWARD, FFT_INVERSE = -1, 1
 FFT_GPU_CUDA, FFT_GPU_AUTO = 1, -1

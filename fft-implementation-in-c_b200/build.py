@@ -7,13 +7,15 @@ from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
-OBJ = os.path.join(HERE, "build")
-LIB = os.path.join(HERE, "lib", "libfft_b200.so")
+# FFTB200_VARIANT=<name> + FFTB200_NVCC_EXTRA="-D..." build an A/B library lib/ab_<name>.so in its own object dir
+_VAR = os.environ.get("FFTB200_VARIANT", "")
+OBJ = os.path.join(HERE, "build" + ("_" + _VAR if _VAR else ""))
+LIB = os.path.join(HERE, "lib", "ab_%s.so" % _VAR if _VAR else "libfft_b200.so")
 
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 GCC = "/usr/bin/gcc"
 NVCC_FLAGS = ["-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3",
-              "-Xcompiler", "-fPIC", "-ccbin", "/usr/bin/g++"]
+              "-Xcompiler", "-fPIC", "-ccbin", "/usr/bin/g++"] + os.environ.get("FFTB200_NVCC_EXTRA", "").split()
 # The host tables replicate the reference's rounding sequence explicitly (host/ref_twiddle.c): no
 # fast-math, no implicit FMA contraction. x86-64-v3 = AVX2+FMA so fma() is one instruction.
 HOST_FLAGS = ["-O2", "-std=c99", "-march=x86-64-v3", "-ffp-contract=off", "-fPIC", "-Wall", "-Wextra",

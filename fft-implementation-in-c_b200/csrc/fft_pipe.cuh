@@ -22,8 +22,14 @@
 // (radix2_dit.c:93,109) is still within 3e-14 (relative L2 of the whole transform) of correctly rounded
 // twiddles - SURVEY.md 7.0 "hybrid". The kernel therefore reads the ACCURATE per-stage table (same layout
 // as the reference-recurrence table), which has the symmetry w[q + m/4] = -i * w[q]; only 8 of the 15
-// twiddles of a radix-16 butterfly are loaded, the other 7 are free sign/swap variants. The last
-// sub-pass's 8 twiddles depend only on the thread index and stay in registers for the whole kernel.
+// twiddles of a radix-16 butterfly are needed, the other 7 are free sign/swap variants. The middle
+// sub-pass reads its 8 from a 2 KB shared table; the last sub-pass's twiddles depend only on the thread
+// index: w^8, w^4, w^2, w stay in registers for the whole kernel, the other four are w^2 * W8 and
+// w * {W16, W8, W16^3}, rebuilt per tile (16 FP64 instructions).
+//
+// Measured alternatives (same box A/B, N = 4096 x 65536, ms): this form 1.31-1.32; all 8 last-pass twiddles
+// in registers 1.51 (spills on the loop-carried path); the 4 powers in a per-thread shared table 1.43 (the
+// LSU / MIO queue is the most loaded pipe: every extra LDS costs more than 16 extra DFMA).
 #pragma once
 #include "fft_tile.cuh"
 
