@@ -178,11 +178,16 @@ struct Pass {
     const KernelInfo* k;   // nullptr: persistent TMA kernel fft_pipe_kernel<log_p>
     int log_p;
     int log_m;
-    long long ntiles;
+    int nt;        // whole-transform kernels: transforms per tile (tiles = ceil(nbatch / nt)); else 0
+    int shift;     // strided / last kernels: log2 tiles per transform (tiles = nbatch << shift)
     int src, dst;
     int final_pass;
-    int grid;
+    int grid_max;  // persistent grid: SMs x resident CTAs
 };
+
+static long long pass_tiles(const Pass& ps, long long nbatch) {
+    return ps.nt ? (nbatch + ps.nt - 1) / ps.nt : nbatch << ps.shift;
+}
 
 struct fftb200_plan {
     int device = 0;
@@ -192,14 +197,17 @@ struct fftb200_plan {
     std::vector<Pass> passes;  // forward or inverse c2c of length m over `batch`
     const cd* tab = nullptr;
     const cd* acc = nullptr;   // accurate tables (nullptr: reference-recurrence tables everywhere)
-    cd* scratch = nullptr;     // ping-pong buffer for multi-pass plans
+    cd* scratch = nullptr;     // ping-pong buffer for multi-pass plans, allocated on first use
+    size_t scratch_elems = 0;
     cd* work = nullptr;        // Bluestein / R2C: padded complex work array, m * batch
     cd* chirp = nullptr;       // Bluestein: n entries
     cd* fb = nullptr;          // Bluestein: FFT_m of the wrapped chirp
     // host staging (exec_host)
-    cd* d_stage_in = nullptr;
-    cd* d_stage_out = nullptr;
-    cudaStream_t stream = nullptr, stream2 = nullptr;
+    enum { NSTAGE = 3 };
+    cd* d_ring[NSTAGE] = {nullptr, nullptr, nullptr};   // chunked host pipeline: in-place staging buffers
+    int ring_batch = 0;                                  // transforms per staging buffer
+    cudaEvent_t ev_up[NSTAGE] = {}, ev_run[NSTAGE] = {}, ev_down[NSTAGE] = {};
+    cudaStream_t stream = nullptr, s_up = nullptr, s_down = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     int launches = 0;
     std::string desc;
@@ -246,13 +254,11 @@ static int build_passes(fftb200_plan* p, DeviceState* ds) {
     if (np == 1 && L >= 9 && L <= 12 && p->acc && !getenv("FFTB200_NO_PIPE")) {
         Pass ps;
         ps.k = nullptr; ps.log_p = L; ps.log_m = 0;
-        const int nt = PIPE_TILE >> L;
-        ps.ntiles = ((long long)p->batch + nt - 1) / nt;
+        ps.nt = PIPE_TILE >> L; ps.shift = 0;
         ps.src = BUF_IN; ps.dst = BUF_OUT; ps.final_pass = 1;
         for (int iv = 0; iv < 2; iv++)
             CU(cudaFuncSetAttribute(pipe_func(L, iv), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PIPE_SMEM));
-        long long g = ds->sms < ps.ntiles ? ds->sms : ps.ntiles;
-        ps.grid = (int)(g < 1 ? 1 : g);
+        ps.grid_max = ds->sms;
         p->passes.push_back(ps);
         char b[64];
         snprintf(b, sizeof(b), "P%d(tma ring %d x 64KB, 2x256 thr)", L, PIPE_STAGES);
@@ -270,15 +276,16 @@ static int build_passes(fftb200_plan* p, DeviceState* ds) {
         ps.k = find_kernel(mode, lp, mode == MODE_CONTIG ? 1 : (mode == MODE_STRIDED ? (i == 0) : 0));
         if (!ps.k) return fail("no kernel variant for mode %d, 2^%d points", mode, lp);
         ps.log_m = log_m;
+        ps.nt = 0; ps.shift = 0;
         if (mode == MODE_CONTIG) {
-            ps.ntiles = ((long long)p->batch + ps.k->nt - 1) / ps.k->nt;
+            ps.nt = ps.k->nt;
         } else if (mode == MODE_STRIDED) {
             const int log_rest = L - log_m - lp;
             if (log_rest < ps.k->logc) return fail("pass split leaves too few columns");
-            ps.ntiles = (long long)p->batch << (log_rest - ps.k->logc + log_m);
+            ps.shift = log_rest - ps.k->logc + log_m;
         } else {
             if (log_m < ps.k->logc) return fail("last pass too wide");
-            ps.ntiles = (long long)p->batch << (log_m - ps.k->logc);
+            ps.shift = log_m - ps.k->logc;
         }
         // ping-pong so that the final pass lands in OUT; the first pass always reads IN
         ps.src = (i == 0) ? BUF_IN : (((np - 1 - (i - 1)) % 2 == 0) ? BUF_OUT : BUF_SCRATCH);
@@ -288,43 +295,50 @@ static int build_passes(fftb200_plan* p, DeviceState* ds) {
         int occ = 0;
         CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ps.k->func, ps.k->threads, ps.k->smem));
         if (occ < 1) return fail("kernel variant does not fit on an SM");
-        long long g = persistent ? (long long)ds->sms * occ : ps.ntiles;
-        if (g > ps.ntiles) g = ps.ntiles;
-        if (g > 0x7fffffffLL) g = 0x7fffffffLL;
-        if (g < 1) g = 1;
-        ps.grid = (int)g;
+        ps.grid_max = persistent ? ds->sms * occ : 0x7fffffff;
         p->passes.push_back(ps);
         char b[64];
         snprintf(b, sizeof(b), "%s%c%d(occ%d)", i ? "+" : "", mode == MODE_CONTIG ? 'C' : mode == MODE_STRIDED ? (i == 0 ? 'F' : 'M') : 'L', lp, occ);
         p->desc += b;
         log_m += lp;
     }
-    if (np > 1) {
-        p->scratch = (cd*)fftb200_malloc(sizeof(cd) * ((size_t)p->batch << L));
-        if (!p->scratch) return -1;
-    }
+    return 0;
+}
+
+static int ensure_scratch(fftb200_plan* p, long long nbatch) {
+    if (p->passes.size() < 2) return 0;
+    const size_t need = (size_t)nbatch << p->log_n;
+    if (p->scratch_elems >= need) return 0;
+    if (p->scratch) { CU(cudaStreamSynchronize(p->stream)); cudaFree(p->scratch); p->scratch = nullptr; p->scratch_elems = 0; }
+    p->scratch = (cd*)fftb200_malloc(sizeof(cd) * need);
+    if (!p->scratch) return -1;
+    p->scratch_elems = need;
     return 0;
 }
 
 // Enqueue the power-of-two c2c passes: `inverse` selects conjugated twiddles and the 1/m scale.
-static int enqueue_c2c(fftb200_plan* p, const cd* in, cd* out, int inverse) {
+static int enqueue_c2c(fftb200_plan* p, const cd* in, cd* out, int inverse, long long nbatch) {
+    if (nbatch <= 0) return 0;
+    if (ensure_scratch(p, nbatch) != 0) return -1;
     for (const Pass& ps : p->passes) {
+        const long long ntiles = pass_tiles(ps, nbatch);
+        const int grid = (int)(ntiles < ps.grid_max ? ntiles : ps.grid_max);
         if (!ps.k) {
             PipeArgs pa;
             pa.in = in; pa.out = out; pa.tab = p->acc;
-            pa.ntiles = ps.ntiles; pa.batch = p->batch;
+            pa.ntiles = ntiles; pa.batch = nbatch;
             pa.inverse = inverse; pa.scale = 1.0 / (double)p->m;
-            launch_pipe(ps.log_p, pa, ps.grid, p->stream);
+            launch_pipe(ps.log_p, pa, grid, p->stream);
             continue;
         }
         TileArgs a;
         const cd* src = ps.src == BUF_IN ? in : ps.src == BUF_OUT ? out : p->scratch;
         cd* dst = ps.dst == BUF_OUT ? out : p->scratch;
         a.in = src; a.out = dst; a.tab = p->tab;
-        a.ntiles = ps.ntiles; a.batch = p->batch;
+        a.ntiles = ntiles; a.batch = nbatch;
         a.log_n = p->log_n; a.log_m = ps.log_m;
         a.inverse = inverse; a.scale = 1.0 / (double)p->m; a.final_pass = ps.final_pass;
-        ps.k->launch(a, ps.grid, p->stream);
+        ps.k->launch(a, grid, p->stream);
     }
     CU(cudaGetLastError());
     return 0;
@@ -389,7 +403,8 @@ extern "C" int fftb200_plan_create(fftb200_plan** out, const fftb200_plan_desc* 
         } else { rc = fail("plan_create: unknown kind %d", d->kind); break; }
         p->log_n = ilog2(p->m);
         if ((rc = cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking)) != 0) { rc = fail("cudaStreamCreate failed"); break; }
-        if (cudaStreamCreateWithFlags(&p->stream2, cudaStreamNonBlocking) != cudaSuccess) { rc = fail("cudaStreamCreate failed"); break; }
+        if (cudaStreamCreateWithFlags(&p->s_up, cudaStreamNonBlocking) != cudaSuccess ||
+            cudaStreamCreateWithFlags(&p->s_down, cudaStreamNonBlocking) != cudaSuccess) { rc = fail("cudaStreamCreate failed"); break; }
         if (cudaEventCreate(&p->ev0) != cudaSuccess || cudaEventCreate(&p->ev1) != cudaSuccess) { rc = fail("cudaEventCreate failed"); break; }
         if ((rc = upload_table(p, ds, d, p->m)) != 0) break;
         if ((rc = upload_accurate(p, ds, d)) != 0) break;
@@ -411,23 +426,11 @@ extern "C" int fftb200_plan_create(fftb200_plan** out, const fftb200_plan_desc* 
             if (!p->work || !p->chirp || !p->fb) { rc = -1; break; }
             if (cudaMemcpy(p->chirp, d->chirp, sizeof(cd) * (size_t)p->n, cudaMemcpyHostToDevice) != cudaSuccess ||
                 cudaStreamSynchronize(cudaStreamLegacy) != cudaSuccess) { rc = fail("chirp upload failed"); break; }
-            // b[k] = chirp[k], b[m-k] = chirp[k] (bluestein.c:116-121); FB = FFT_m(b), cached in the plan.
-            // The sub-plan is built for the whole batch; a single-transform view of it computes FB.
-            {
-                const int save_batch = p->batch;
-                std::vector<Pass> save = p->passes;
-                cd* save_scratch = p->scratch;
-                p->batch = 1; p->passes.clear(); p->scratch = nullptr; std::string sd = p->desc;
-                rc = build_passes(p, ds);
-                if (rc == 0) {
-                    bluestein_wrap_kernel<<<(unsigned)((m + 255) / 256), 256, 0, p->stream>>>(p->fb, p->chirp, p->n, p->m);
-                    rc = enqueue_c2c(p, p->fb, p->fb, 0);
-                    if (rc == 0 && cudaStreamSynchronize(p->stream) != cudaSuccess) rc = fail("Bluestein kernel spectrum failed: %s", cudaGetErrorString(cudaGetLastError()));
-                }
-                if (p->scratch) cudaFree(p->scratch);
-                p->batch = save_batch; p->passes = save; p->scratch = save_scratch; p->desc = sd;
-                if (rc != 0) break;
-            }
+            // b[k] = chirp[k], b[m-k] = chirp[k] (bluestein.c:116-121); FB = FFT_m(b), cached in the plan
+            bluestein_wrap_kernel<<<(unsigned)((m + 255) / 256), 256, 0, p->stream>>>(p->fb, p->chirp, p->n, p->m);
+            rc = enqueue_c2c(p, p->fb, p->fb, 0, 1);
+            if (rc == 0 && cudaStreamSynchronize(p->stream) != cudaSuccess) rc = fail("Bluestein kernel spectrum failed: %s", cudaGetErrorString(cudaGetLastError()));
+            if (rc != 0) break;
             p->launches = 2 * (int)p->passes.size() + 3;
         }
     } while (0);
@@ -436,33 +439,40 @@ extern "C" int fftb200_plan_create(fftb200_plan** out, const fftb200_plan_desc* 
     return 0;
 }
 
-extern "C" int fftb200_plan_exec_async(fftb200_plan* p, const void* d_in, void* d_out) {
-    if (!p || !d_in || !d_out) return fail("plan_exec: null argument");
+static unsigned grid_for(size_t total) {
+    const size_t b = (total + 255) / 256;
+    return (unsigned)(b > (1u << 20) ? (1u << 20) : (b ? b : 1));
+}
+
+// Enqueue the plan's transform over the first `nbatch` transforms of d_in / d_out on the plan's stream.
+static int exec_range(fftb200_plan* p, const void* d_in, void* d_out, long long nbatch) {
     const int inverse = p->dir > 0;
-    if (p->kind == FFTB200_C2C) return enqueue_c2c(p, (const cd*)d_in, (cd*)d_out, inverse);
-    const size_t m = (size_t)p->m, n = (size_t)p->n, total = m * (size_t)p->batch;
-    unsigned blocks = (unsigned)((total + 255) / 256 > (1u << 20) ? (1u << 20) : (total + 255) / 256);
+    if (p->kind == FFTB200_C2C) return enqueue_c2c(p, (const cd*)d_in, (cd*)d_out, inverse, nbatch);
+    const size_t m = (size_t)p->m, n = (size_t)p->n, total = m * (size_t)nbatch;
     if (p->kind == FFTB200_R2C) {
-        r2c_promote_kernel<<<blocks, 256, 0, p->stream>>>(p->work, (const double*)d_in, total);
-        if (enqueue_c2c(p, p->work, p->work, 0) != 0) return -1;
-        const size_t nh = n / 2 + 1, tot_out = nh * (size_t)p->batch;
-        unsigned b2 = (unsigned)((tot_out + 255) / 256 > (1u << 20) ? (1u << 20) : (tot_out + 255) / 256);
-        r2c_extract_kernel<<<b2, 256, 0, p->stream>>>((cd*)d_out, p->work, n, nh, tot_out);
+        r2c_promote_kernel<<<grid_for(total), 256, 0, p->stream>>>(p->work, (const double*)d_in, total);
+        if (enqueue_c2c(p, p->work, p->work, 0, nbatch) != 0) return -1;
+        const size_t nh = n / 2 + 1, tot_out = nh * (size_t)nbatch;
+        r2c_extract_kernel<<<grid_for(tot_out), 256, 0, p->stream>>>((cd*)d_out, p->work, n, nh, tot_out);
         CU(cudaGetLastError());
         return 0;
     }
     // Bluestein (bluestein.c:107-148): a = x * conj(chirp) zero-padded to m; A = FFT(a) * FB; inverse FFT;
     // y = a * conj(chirp) (and 1/n for the inverse direction).
-    bluestein_pre_kernel<<<blocks, 256, 0, p->stream>>>(p->work, (const cd*)d_in, p->chirp, p->n, p->m, total);
-    if (enqueue_c2c(p, p->work, p->work, 0) != 0) return -1;
-    pointwise_mul_kernel<<<blocks, 256, 0, p->stream>>>(p->work, p->work, p->fb, total, m);
-    if (enqueue_c2c(p, p->work, p->work, 1) != 0) return -1;
-    const size_t tot_out = n * (size_t)p->batch;
-    unsigned b2 = (unsigned)((tot_out + 255) / 256 > (1u << 20) ? (1u << 20) : (tot_out + 255) / 256);
-    bluestein_post_kernel<<<b2, 256, 0, p->stream>>>((cd*)d_out, p->work, p->chirp, p->n, p->m, tot_out,
-                                                      inverse ? 1.0 / (double)p->n : 1.0);
+    bluestein_pre_kernel<<<grid_for(total), 256, 0, p->stream>>>(p->work, (const cd*)d_in, p->chirp, p->n, p->m, total);
+    if (enqueue_c2c(p, p->work, p->work, 0, nbatch) != 0) return -1;
+    pointwise_mul_kernel<<<grid_for(total), 256, 0, p->stream>>>(p->work, p->work, p->fb, total, m);
+    if (enqueue_c2c(p, p->work, p->work, 1, nbatch) != 0) return -1;
+    const size_t tot_out = n * (size_t)nbatch;
+    bluestein_post_kernel<<<grid_for(tot_out), 256, 0, p->stream>>>((cd*)d_out, p->work, p->chirp, p->n, p->m, tot_out,
+                                                                   inverse ? 1.0 / (double)p->n : 1.0);
     CU(cudaGetLastError());
     return 0;
+}
+
+extern "C" int fftb200_plan_exec_async(fftb200_plan* p, const void* d_in, void* d_out) {
+    if (!p || !d_in || !d_out) return fail("plan_exec: null argument");
+    return exec_range(p, d_in, d_out, p->batch);
 }
 
 extern "C" int fftb200_plan_sync(fftb200_plan* p) {
@@ -477,23 +487,49 @@ extern "C" int fftb200_plan_exec(fftb200_plan* p, const void* d_in, void* d_out)
 }
 
 // Host-pointer execution (the H2D -> execute -> D2H sequence of algorithms/auto/fft_auto.c:278-280 and
-// gpu/fft_cuda.cu:214-252). Device staging buffers live in the plan.
+// gpu/fft_cuda.cu:214-252), pipelined: the batch is cut into chunks of whole transforms; chunk c is uploaded
+// on one stream while chunk c-1 is transformed in place on the plan's stream and chunk c-2 is downloaded on
+// a third stream, through a ring of three device staging buffers owned by the plan. PCIe is full duplex, so
+// with pinned host memory (fft_alloc_complex / fftb200_host_alloc) the job takes max(upload, download)
+// instead of their sum; pageable memory works too but serialises inside the driver.
 extern "C" int fftb200_plan_exec_host(fftb200_plan* p, const void* h_in, void* h_out) {
     if (!p || !h_in || !h_out) return fail("plan_exec_host: null argument");
-    const size_t in_bytes = (p->kind == FFTB200_R2C ? sizeof(double) : sizeof(cd)) * (size_t)p->n * (size_t)p->batch;
-    const size_t out_elems = (p->kind == FFTB200_R2C ? (size_t)(p->n / 2 + 1) : (size_t)p->n) * (size_t)p->batch;
-    if (!p->d_stage_in) {
-        p->d_stage_in = (cd*)fftb200_malloc(in_bytes > out_elems * sizeof(cd) ? in_bytes : out_elems * sizeof(cd));
-        if (!p->d_stage_in) return -1;
+    const size_t in_per = (p->kind == FFTB200_R2C ? sizeof(double) : sizeof(cd)) * (size_t)p->n;      // bytes / transform
+    const size_t out_per = sizeof(cd) * (p->kind == FFTB200_R2C ? (size_t)(p->n / 2 + 1) : (size_t)p->n);
+    const size_t per = in_per > out_per ? in_per : out_per;
+    if (!p->d_ring[0]) {
+        size_t target = 32u << 20;                       // bytes per chunk
+        if (const char* e = getenv("FFTB200_CHUNK_MB")) target = (size_t)atol(e) << 20;
+        long long cb = (long long)(target / per);
+        if (cb < 1) cb = 1;
+        if (cb > p->batch) cb = p->batch;
+        for (int i = 0; i < fftb200_plan::NSTAGE; i++) {
+            p->d_ring[i] = (cd*)fftb200_malloc(per * (size_t)cb);
+            if (!p->d_ring[i]) return -1;
+            if (cudaEventCreateWithFlags(&p->ev_up[i], cudaEventDisableTiming) != cudaSuccess ||
+                cudaEventCreateWithFlags(&p->ev_run[i], cudaEventDisableTiming) != cudaSuccess ||
+                cudaEventCreateWithFlags(&p->ev_down[i], cudaEventDisableTiming) != cudaSuccess) return fail("cudaEventCreate failed");
+        }
+        p->ring_batch = (int)cb;
     }
-    void* d_out = p->d_stage_in;
-    if (p->kind == FFTB200_R2C) {
-        if (!p->d_stage_out) { p->d_stage_out = (cd*)fftb200_malloc(out_elems * sizeof(cd)); if (!p->d_stage_out) return -1; }
-        d_out = p->d_stage_out;
+    const long long cb = p->ring_batch;
+    const char* src = (const char*)h_in;
+    char* dst = (char*)h_out;
+    int c = 0;
+    for (long long b0 = 0; b0 < p->batch; b0 += cb, c++) {
+        const long long nb = p->batch - b0 < cb ? p->batch - b0 : cb;
+        const int r = c % fftb200_plan::NSTAGE;
+        if (c >= fftb200_plan::NSTAGE) CU(cudaStreamWaitEvent(p->s_up, p->ev_down[r], 0));   // staging buffer drained
+        CU(cudaMemcpyAsync(p->d_ring[r], src + (size_t)b0 * in_per, in_per * (size_t)nb, cudaMemcpyHostToDevice, p->s_up));
+        CU(cudaEventRecord(p->ev_up[r], p->s_up));
+        CU(cudaStreamWaitEvent(p->stream, p->ev_up[r], 0));
+        if (exec_range(p, p->d_ring[r], p->d_ring[r], nb) != 0) return -1;
+        CU(cudaEventRecord(p->ev_run[r], p->stream));
+        CU(cudaStreamWaitEvent(p->s_down, p->ev_run[r], 0));
+        CU(cudaMemcpyAsync(dst + (size_t)b0 * out_per, p->d_ring[r], out_per * (size_t)nb, cudaMemcpyDeviceToHost, p->s_down));
+        CU(cudaEventRecord(p->ev_down[r], p->s_down));
     }
-    CU(cudaMemcpyAsync(p->d_stage_in, h_in, in_bytes, cudaMemcpyHostToDevice, p->stream));
-    if (fftb200_plan_exec_async(p, p->d_stage_in, d_out) != 0) return -1;
-    CU(cudaMemcpyAsync(h_out, d_out, out_elems * sizeof(cd), cudaMemcpyDeviceToHost, p->stream));
+    CU(cudaStreamSynchronize(p->s_down));
     CU(cudaStreamSynchronize(p->stream));
     return 0;
 }
@@ -501,16 +537,22 @@ extern "C" int fftb200_plan_exec_host(fftb200_plan* p, const void* h_in, void* h
 extern "C" void fftb200_plan_destroy(fftb200_plan* p) {
     if (!p) return;
     if (p->stream) cudaStreamSynchronize(p->stream);
+    if (p->s_down) cudaStreamSynchronize(p->s_down);
     if (p->scratch) cudaFree(p->scratch);
     if (p->work) cudaFree(p->work);
     if (p->chirp) cudaFree(p->chirp);
     if (p->fb) cudaFree(p->fb);
-    if (p->d_stage_in) cudaFree(p->d_stage_in);
-    if (p->d_stage_out) cudaFree(p->d_stage_out);
+    for (int i = 0; i < fftb200_plan::NSTAGE; i++) {
+        if (p->d_ring[i]) cudaFree(p->d_ring[i]);
+        if (p->ev_up[i]) cudaEventDestroy(p->ev_up[i]);
+        if (p->ev_run[i]) cudaEventDestroy(p->ev_run[i]);
+        if (p->ev_down[i]) cudaEventDestroy(p->ev_down[i]);
+    }
     if (p->ev0) cudaEventDestroy(p->ev0);
     if (p->ev1) cudaEventDestroy(p->ev1);
     if (p->stream) cudaStreamDestroy(p->stream);
-    if (p->stream2) cudaStreamDestroy(p->stream2);
+    if (p->s_up) cudaStreamDestroy(p->s_up);
+    if (p->s_down) cudaStreamDestroy(p->s_down);
     delete p;
 }
 

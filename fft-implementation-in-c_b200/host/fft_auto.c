@@ -16,6 +16,7 @@
 #include "../../include/fft_gpu.h"
 #include "../../include/fftb200.h"
 #include "ref_twiddle.h"
+#include <pthread.h>
 
 fftb200_plan* fftb200_host_make_plan(int n, int batch, int direction, int kind); /* fft_gpu.c */
 
@@ -78,12 +79,13 @@ void fft_destroy_plan(fft_plan_t plan) {
     free(plan);
 }
 
+/* One-shot transform (reference fft_auto.c:325-333: plan, execute, destroy). The engine plan of the last
+ * shape is kept by the host library, so a loop of fft_auto calls builds tables / streams / staging once. */
+int fftb200_host_exec_cached(const void* in, void* out, int n, int batch, int direction, int kind); /* fft_gpu.c */
+
 int fft_auto(complex_t* in, complex_t* out, int n, int sign) {
-    fft_plan_t plan = fft_plan_dft_1d(n, in, out, sign, FFT_ESTIMATE);
-    if (!plan) return -1;
-    fft_execute(plan);
-    fft_destroy_plan(plan);
-    return 0;
+    if (n <= 0 || !in || !out) return -1;
+    return fftb200_host_exec_cached(in, out, n, 1, sign < 0 ? -1 : 1, is_power_of_two(n) ? FFTB200_C2C : FFTB200_BLUESTEIN);
 }
 
 /* stubs in the reference (fft_auto.c:405-415) */
@@ -114,16 +116,53 @@ unsigned fft_get_hardware_capabilities(void) {
 
 void fft_plan_with_nthreads(int nthreads) { g_num_threads = nthreads; }
 
-complex_t* fft_alloc_complex(size_t n) {
+/* Allocators (reference fft_auto.c:352-384: 64-byte posix_memalign). With a GPU present the memory is
+ * page-locked (cudaMallocHost, 256-byte aligned at least), so fft_execute / fft_gpu_dft_1d_batch on these
+ * buffers upload and download by DMA at full PCIe rate and overlap the two directions; fft_free tells the
+ * two kinds apart through a small registry. Without a GPU they are plain aligned allocations. */
+struct pin_node { void* p; struct pin_node* next; };
+static struct pin_node* g_pins = NULL;
+static pthread_mutex_t g_pin_mu = PTHREAD_MUTEX_INITIALIZER;
+
+static void* alloc_bytes(size_t bytes) {
+    if (bytes == 0) bytes = 64;
+    if (bytes >= (1u << 16) && fft_gpu_available() && !getenv("FFTB200_NO_PINNED")) {
+        void* p = fftb200_host_alloc(bytes);
+        if (p) {
+            struct pin_node* nd = (struct pin_node*)malloc(sizeof(*nd));
+            if (nd) {
+                nd->p = p;
+                pthread_mutex_lock(&g_pin_mu);
+                nd->next = g_pins; g_pins = nd;
+                pthread_mutex_unlock(&g_pin_mu);
+                return p;
+            }
+            fftb200_host_free(p);
+        }
+    }
     void* p = NULL;
-    if (posix_memalign(&p, 64, (n ? n : 1) * sizeof(complex_t)) != 0) return NULL;
-    return (complex_t*)p;
+    if (posix_memalign(&p, 64, bytes) != 0) return NULL;
+    return p;
 }
-double* fft_alloc_real(size_t n) {
-    void* p = NULL;
-    if (posix_memalign(&p, 64, (n ? n : 1) * sizeof(double)) != 0) return NULL;
-    return (double*)p;
+
+complex_t* fft_alloc_complex(size_t n) { return (complex_t*)alloc_bytes(n * sizeof(complex_t)); }
+double* fft_alloc_real(size_t n) { return (double*)alloc_bytes(n * sizeof(double)); }
+
+void fft_free(void* p) {
+    if (!p) return;
+    pthread_mutex_lock(&g_pin_mu);
+    for (struct pin_node** pp = &g_pins; *pp; pp = &(*pp)->next) {
+        if ((*pp)->p == p) {
+            struct pin_node* nd = *pp;
+            *pp = nd->next;
+            pthread_mutex_unlock(&g_pin_mu);
+            free(nd);
+            fftb200_host_free(p);
+            return;
+        }
+    }
+    pthread_mutex_unlock(&g_pin_mu);
+    free(p);
 }
-void fft_free(void* p) { free(p); }
 
 const char* fft_version(void) { return "FFT Library v2.0.0 - Automatic Algorithm Selection (B200 sm_100a engine)"; }

@@ -12,6 +12,7 @@
 #include "../../include/fftb200.h"
 #include "../../include/fftb200_ext.h"
 #include "ref_twiddle.h"
+#include <pthread.h>
 
 struct fft_gpu_memory {
     void* dptr;
@@ -40,7 +41,10 @@ int fft_gpu_init(fft_gpu_backend_t backend) {
     return 0;
 }
 
+static void cache_drop(void);
+
 void fft_gpu_cleanup(void) {
+    cache_drop();
     if (g_backend == FFT_GPU_CUDA) fftb200_device_reset();
     g_backend = FFT_GPU_NONE;
 }
@@ -128,14 +132,39 @@ void fft_gpu_destroy_plan(fft_gpu_plan_t plan) {
     free(plan);
 }
 
+/* The host-pointer conveniences keep their last engine plan (tables, streams, staging ring): a caller that
+ * loops over fft_gpu_dft_1d_batch with one shape - the reference's usage, gpu/fft_gpu.c:366-374 - pays for plan
+ * construction once. One entry, guarded by a mutex that is held while the plan runs. */
+static struct { fftb200_plan* plan; int n, batch, dir, kind, device; } g_cache = {NULL, 0, 0, 0, 0, -1};
+static pthread_mutex_t g_cache_mu = PTHREAD_MUTEX_INITIALIZER;
+
+static void cache_drop(void) {
+    pthread_mutex_lock(&g_cache_mu);
+    if (g_cache.plan) fftb200_plan_destroy(g_cache.plan);
+    g_cache.plan = NULL;
+    pthread_mutex_unlock(&g_cache_mu);
+}
+
+int fftb200_host_exec_cached(const void* in, void* out, int n, int batch, int direction, int kind) {
+    if (ensure_init() != 0) return -1;
+    const int dev = fftb200_get_device();
+    pthread_mutex_lock(&g_cache_mu);
+    if (!g_cache.plan || g_cache.n != n || g_cache.batch != batch || g_cache.dir != direction || g_cache.kind != kind ||
+        g_cache.device != dev) {
+        if (g_cache.plan) fftb200_plan_destroy(g_cache.plan);
+        g_cache.plan = fftb200_host_make_plan(n, batch, direction, kind);
+        g_cache.n = n; g_cache.batch = batch; g_cache.dir = direction; g_cache.kind = kind; g_cache.device = dev;
+    }
+    int rc = g_cache.plan ? fftb200_plan_exec_host(g_cache.plan, in, out) : -1;
+    if (rc != 0 && g_cache.plan) report("host execute");
+    pthread_mutex_unlock(&g_cache_mu);
+    return rc == 0 ? 0 : -1;
+}
+
 int fft_gpu_dft_1d_batch(complex_t* in, complex_t* out, int n, int batch, fft_direction direction) {
     if (!in || !out || n <= 0 || batch <= 0) return -1;
-    fftb200_plan* p = fftb200_host_make_plan(n, batch, (int)direction, is_power_of_two(n) ? FFTB200_C2C : FFTB200_BLUESTEIN);
-    if (!p) return -1;
-    int rc = fftb200_plan_exec_host(p, in, out);
-    if (rc != 0) report("dft_1d_batch");
-    fftb200_plan_destroy(p);
-    return rc == 0 ? 0 : -1;
+    return fftb200_host_exec_cached(in, out, n, batch, (int)direction < 0 ? -1 : 1,
+                                    is_power_of_two(n) ? FFTB200_C2C : FFTB200_BLUESTEIN);
 }
 
 int fft_gpu_dft_1d(complex_t* in, complex_t* out, int n, fft_direction direction) {
