@@ -18,6 +18,7 @@
 #include "../../include/fftb200.h"
 #include "fft_aux.cuh"
 #include "fft_catalog.h"
+#include "fft_fused.cuh"
 #include "fft_pipe.cuh"
 
 using namespace fftb200;
@@ -175,7 +176,8 @@ enum { BUF_IN = 0, BUF_OUT = 1, BUF_SCRATCH = 2 };
 enum { ACC_N = 8192 };  // accurate tables cover stages m <= 8192 (hybrid twiddles)
 
 struct Pass {
-    const KernelInfo* k;   // nullptr: persistent TMA kernel fft_pipe_kernel<log_p>
+    const KernelInfo* k;   // nullptr: persistent TMA kernel fft_pipe_kernel<log_p>, or the fused kernel when fused_lm > 0
+    int fused_lm = 0, fused_lr = 0;   // fft_fused_kernel<fused_lm, fused_lr>: both passes in one launch
     int log_p;
     int log_m;
     int nt;        // whole-transform kernels: transforms per tile (tiles = ceil(nbatch / nt)); else 0
@@ -199,6 +201,11 @@ struct fftb200_plan {
     const cd* acc = nullptr;   // accurate tables (nullptr: reference-recurrence tables everywhere)
     cd* scratch = nullptr;     // ping-pong buffer for multi-pass plans, allocated on first use
     size_t scratch_elems = 0;
+    cd* fscratch = nullptr;    // fused plans: L2-resident ring of `slots` groups of transforms
+    size_t fscratch_elems = 0;
+    int* fflags = nullptr;     // fused plans: per-group completion counters
+    size_t fflags_count = 0;
+    cd fdtw[3][16];            // fused plans: pass-B derived-twiddle constants (fft_fused.cuh: fused_twiddles)
     cd* work = nullptr;        // Bluestein / R2C: padded complex work array, m * batch
     cd* chirp = nullptr;       // Bluestein: n entries
     cd* fb = nullptr;          // Bluestein: FFT_m of the wrapped chirp
@@ -265,6 +272,27 @@ static int build_passes(fftb200_plan* p, DeviceState* ds) {
         p->desc += b;
         return 0;
     }
+    if (L >= 13 && L <= 20 && p->acc && !getenv("FFTB200_NO_FUSED")) {
+        int lm = (L + 1) / 2, lr = L / 2;
+        if (const char* e = getenv("FFTB200_FUSED_LM")) { lm = atoi(e); lr = L - lm; }
+        if (fused_func(lm, lr, 0)) {
+            Pass ps;
+            ps.k = nullptr; ps.fused_lm = lm; ps.fused_lr = lr;
+            ps.log_p = L; ps.log_m = 0; ps.nt = 0; ps.shift = 0;
+            ps.src = BUF_IN; ps.dst = BUF_OUT; ps.final_pass = 1;
+            for (int iv = 0; iv < 2; iv++)
+                CU(cudaFuncSetAttribute(fused_func(lm, lr, iv), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FUSED_SMEM));
+            int occ = 0;
+            CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fused_func(lm, lr, 0), FUSED_THREADS, FUSED_SMEM));
+            if (occ < 1) return fail("fused kernel does not fit on an SM");
+            ps.grid_max = ds->sms;   // every CTA must be resident: the passes synchronise through global counters
+            p->passes.push_back(ps);
+            char b[96];
+            snprintf(b, sizeof(b), "Z%d+%d(fused two-pass, tma ring, L2-resident intermediate)", lm, lr);
+            p->desc += b;
+            return 0;
+        }
+    }
     for (int i = 0; i < np; i++) {
         Pass ps;
         const int lp = sizes[i];
@@ -305,6 +333,109 @@ static int build_passes(fftb200_plan* p, DeviceState* ds) {
     return 0;
 }
 
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link against libcuda)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* f = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)f;
+        else
+            cudaGetLastError();
+    });
+    return fn;
+}
+
+// Enqueue the fused two-pass kernel (fft_fused.cuh) for `nbatch` transforms.
+static int enqueue_fused(fftb200_plan* p, const Pass& ps, const cd* in, cd* out, int inverse, long long nbatch) {
+    const int L = p->log_n, lm = ps.fused_lm, lr = ps.fused_lr;
+    const long long tpt = 1LL << (L - 12);                  // 64 KB tiles per transform and pass
+    long long gt = tpt >= 32 ? 1 : 32 / tpt;                // transforms per group: >= 32 tiles (2 MB)
+    if (const char* e = getenv("FFTB200_FUSED_GT")) gt = atol(e);
+    if (gt > nbatch) gt = nbatch;
+    if (gt < 1) gt = 1;
+    const long long T = gt * tpt;
+    long long lag = (3 * ps.grid_max + T - 1) / T;           // ~3 tiles per CTA between the end of A(g) and B(g)
+    if (const char* e = getenv("FFTB200_FUSED_LAG")) lag = atol(e);
+    if (lag < 1) lag = 1;
+    long long slots = lag + 2;
+    while (slots > lag + 1 && slots * T * PIPE_TILE * (long long)sizeof(cd) > (40LL << 20)) slots--;
+    if (const char* e = getenv("FFTB200_FUSED_SLOTS")) slots = atol(e);
+    if (slots < lag + 1) slots = lag + 1;
+    const long long G = (nbatch + gt - 1) / gt;
+    if (slots > G) slots = G > lag + 1 ? G : lag + 1;
+    const size_t need = (size_t)(slots * gt) << L;
+    if (p->fscratch_elems < need) {
+        if (p->fscratch) { CU(cudaStreamSynchronize(p->stream)); cudaFree(p->fscratch); p->fscratch = nullptr; p->fscratch_elems = 0; }
+        p->fscratch = (cd*)fftb200_malloc(sizeof(cd) * need);
+        if (!p->fscratch) return -1;
+        p->fscratch_elems = need;
+    }
+    const size_t nflags = (size_t)(2 * G + 1);
+    if (p->fflags_count < nflags) {
+        if (p->fflags) { CU(cudaStreamSynchronize(p->stream)); cudaFree(p->fflags); p->fflags = nullptr; p->fflags_count = 0; }
+        p->fflags = (int*)fftb200_malloc(sizeof(int) * nflags);
+        if (!p->fflags) return -1;
+        p->fflags_count = nflags;
+    }
+    CU(cudaMemsetAsync(p->fflags, 0, sizeof(int) * nflags, p->stream));
+    // the input seen as a row-major [nbatch * M][R] array of complex doubles; a pass-A tile is the box C x min(M, 256)
+    EncodeTiledFn enc = encode_tiled_fn();
+    if (!enc) return fail("cuTensorMapEncodeTiled is not available from this driver");
+    CUtensorMap tm;
+    const cuuint64_t gdim[2] = {(cuuint64_t)2 << lr, (cuuint64_t)nbatch << lm};
+    const cuuint64_t gstr[1] = {(cuuint64_t)sizeof(cd) << lr};
+    const cuuint32_t box[2] = {(cuuint32_t)2 << (12 - lm), (cuuint32_t)(lm > 8 ? 256 : 1 << lm)};
+    const cuuint32_t estr[2] = {1, 1};
+    int promo = 12 - lm >= 4 ? 2 : 12 - lm >= 3 ? 1 : 0;      // rows of 256 / 128 / 64 bytes
+    if (const char* e = getenv("FFTB200_FUSED_PROMO")) promo = atoi(e);
+    const CUtensorMapL2promotion pr = promo >= 2 ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B : promo == 1 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B
+                                                                                                   : CU_TENSOR_MAP_L2_PROMOTION_NONE;
+    const CUresult r = enc(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, (void*)in, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                           CU_TENSOR_MAP_SWIZZLE_NONE, pr, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled failed (%d)", (int)r);
+    FusedArgs fa;
+    fa.in = in; fa.out = out; fa.scratch = p->fscratch; fa.tab = p->tab; fa.acc = p->acc; fa.flags = p->fflags;
+    fa.nbatch = nbatch; fa.gt = (int)gt; fa.ngroups = (int)G; fa.lag = (int)lag; fa.slots = (int)slots;
+    fa.inverse = inverse; fa.scale = 1.0 / (double)p->m;
+    fa.debug = getenv("FFTB200_FUSED_DEBUG") ? atoi(getenv("FFTB200_FUSED_DEBUG")) : 0;
+    memcpy(fa.dtw, p->fdtw, sizeof(fa.dtw));
+    fa.prof = nullptr;
+#ifdef FUSED_PROF
+    static long long* d_prof = nullptr;
+    if (!d_prof) d_prof = (long long*)fftb200_malloc(sizeof(long long) * 32 * 1024);
+    fa.prof = d_prof;
+#endif
+    const long long items = 2 * nbatch * tpt;
+    const int grid = (int)(items < ps.grid_max ? items : ps.grid_max);
+    if (!launch_fused(lm, lr, fa, tm, grid, p->stream)) return fail("no fused kernel for 2^%d x 2^%d", lm, lr);
+    CU(cudaGetLastError());
+#ifdef FUSED_PROF
+    if (getenv("FFTB200_FUSED_PROF_PRINT")) {
+        CU(cudaStreamSynchronize(p->stream));
+        std::vector<long long> h(32 * grid);
+        CU(cudaMemcpy(h.data(), fa.prof, sizeof(long long) * 32 * grid, cudaMemcpyDeviceToHost));
+        double e = 0, f = 0, tot = 0, tiles = 0, ph[12] = {0};
+        for (int i = 0; i < 2 * grid; i++) {
+            e += h[i * 16]; f += h[i * 16 + 1]; tot += h[i * 16 + 2]; tiles += h[i * 16 + 3];
+            for (int j = 0; j < 12; j++) ph[j] += h[i * 16 + 4 + j];
+        }
+        fprintf(stderr, "fused prof phases per group-tile (all tiles): A: sp0 %.0f sync %.0f sp1 %.0f war+sync %.0f store %.0f signal %.0f | "
+                "B: sp0 %.0f sync %.0f mid+gatherL %.0f sync %.0f tw+bfly+store %.0f signal %.0f\n",
+                ph[0] / tiles, ph[1] / tiles, ph[2] / tiles, ph[3] / tiles, ph[4] / tiles, ph[5] / tiles, ph[6] / tiles, ph[7] / tiles,
+                ph[8] / tiles, ph[9] / tiles, ph[10] / tiles, ph[11] / tiles);
+        fprintf(stderr, "fused prof: per group-tile cycles: total %.0f, empty-wait %.0f, full-wait %.0f, busy %.0f (tiles/group %.1f)\n",
+                tot / tiles, e / tiles, f / tiles, (tot - e - f) / tiles, tiles / (2 * grid));
+    }
+#endif
+    return 0;
+}
+
 static int ensure_scratch(fftb200_plan* p, long long nbatch) {
     if (p->passes.size() < 2) return 0;
     const size_t need = (size_t)nbatch << p->log_n;
@@ -317,12 +448,35 @@ static int ensure_scratch(fftb200_plan* p, long long nbatch) {
 }
 
 // Enqueue the power-of-two c2c passes: `inverse` selects conjugated twiddles and the 1/m scale.
+static int enqueue_c2c_range(fftb200_plan* p, const cd* in, cd* out, int inverse, long long nbatch);
+
 static int enqueue_c2c(fftb200_plan* p, const cd* in, cd* out, int inverse, long long nbatch) {
+    if (nbatch <= 0) return 0;
+    // EXPERIMENT: run multi-pass plans group by group so the intermediate stays in L2
+    if (p->passes.size() >= 2 && getenv("FFTB200_GROUP_MB")) {
+        long long gb = ((long long)atol(getenv("FFTB200_GROUP_MB")) << 20) / ((long long)sizeof(cd) << p->log_n);
+        if (gb < 1) gb = 1;
+        if (gb < nbatch) {
+            for (long long b0 = 0; b0 < nbatch; b0 += gb) {
+                const long long nb = nbatch - b0 < gb ? nbatch - b0 : gb;
+                if (enqueue_c2c_range(p, in + (b0 << p->log_n), out + (b0 << p->log_n), inverse, nb) != 0) return -1;
+            }
+            return 0;
+        }
+    }
+    return enqueue_c2c_range(p, in, out, inverse, nbatch);
+}
+
+static int enqueue_c2c_range(fftb200_plan* p, const cd* in, cd* out, int inverse, long long nbatch) {
     if (nbatch <= 0) return 0;
     if (ensure_scratch(p, nbatch) != 0) return -1;
     for (const Pass& ps : p->passes) {
         const long long ntiles = pass_tiles(ps, nbatch);
         const int grid = (int)(ntiles < ps.grid_max ? ntiles : ps.grid_max);
+        if (ps.fused_lm) {
+            if (enqueue_fused(p, ps, in, out, inverse, nbatch) != 0) return -1;
+            continue;
+        }
         if (!ps.k) {
             PipeArgs pa;
             pa.in = in; pa.out = out; pa.tab = p->acc;
@@ -413,6 +567,20 @@ extern "C" int fftb200_plan_create(fftb200_plan** out, const fftb200_plan_desc* 
         p->desc = head;
         if ((rc = build_passes(p, ds)) != 0) break;
         p->launches = (int)p->passes.size();
+        if (p->passes.size() == 1 && p->passes[0].fused_lm) {
+            // dtw[j][h] = table entry (h << a_tot_j) - 1: stage a_tot_j + s, index q << a_tot_j, h = 2^(s-1) + q
+            if (!d->twiddles || d->table_n < p->m) { rc = fail("fused plan needs the host twiddle table"); break; }
+            const int lm = p->passes[0].fused_lm, lr = p->passes[0].fused_lr;
+            const int rb0 = lr >= 9 ? lr - 8 : lr - 4;
+            const int atot[3] = {lm, lm + rb0, lm + lr - 4};   // first / middle (three sub-passes only) / last
+            const int rad[3] = {rb0, 4, 4};
+            const cd* ht = (const cd*)d->twiddles;
+            for (int j = 0; j < 3; j++)
+                for (int h = 0; h < 16; h++) {
+                    p->fdtw[j][h] = make_double2(1.0, 0.0);
+                    if (h >= 1 && h < (1 << rad[j]) && !(j == 1 && lr < 9)) p->fdtw[j][h] = ht[((size_t)h << atot[j]) - 1];
+                }
+        }
         if (d->kind == FFTB200_R2C) {
             p->work = (cd*)fftb200_malloc(sizeof(cd) * (size_t)p->m * (size_t)p->batch);
             if (!p->work) { rc = -1; break; }
@@ -539,6 +707,8 @@ extern "C" void fftb200_plan_destroy(fftb200_plan* p) {
     if (p->stream) cudaStreamSynchronize(p->stream);
     if (p->s_down) cudaStreamSynchronize(p->s_down);
     if (p->scratch) cudaFree(p->scratch);
+    if (p->fscratch) cudaFree(p->fscratch);
+    if (p->fflags) cudaFree(p->fflags);
     if (p->work) cudaFree(p->work);
     if (p->chirp) cudaFree(p->chirp);
     if (p->fb) cudaFree(p->fb);
