@@ -363,8 +363,8 @@ static int enqueue_fused(fftb200_plan* p, const Pass& ps, const cd* in, cd* out,
     long long lag = (3 * ps.grid_max + T - 1) / T;           // ~3 tiles per CTA between the end of A(g) and B(g)
     if (const char* e = getenv("FFTB200_FUSED_LAG")) lag = atol(e);
     if (lag < 1) lag = 1;
-    long long slots = lag + 2;
-    while (slots > lag + 1 && slots * T * PIPE_TILE * (long long)sizeof(cd) > (40LL << 20)) slots--;
+    long long slots = lag + 3;
+    while (slots > lag + 1 && slots * T * PIPE_TILE * (long long)sizeof(cd) > (48LL << 20)) slots--;
     if (const char* e = getenv("FFTB200_FUSED_SLOTS")) slots = atol(e);
     if (slots < lag + 1) slots = lag + 1;
     const long long G = (nbatch + gt - 1) / gt;
@@ -384,23 +384,29 @@ static int enqueue_fused(fftb200_plan* p, const Pass& ps, const cd* in, cd* out,
         p->fflags_count = nflags;
     }
     CU(cudaMemsetAsync(p->fflags, 0, sizeof(int) * nflags, p->stream));
-    // the input seen as a row-major [nbatch * M][R] array of complex doubles; a pass-A tile is the box C x min(M, 256)
+    // tensor maps (complex double = 2 doubles): the input as a row-major [nbatch * M][R] array, a quarter of a pass-A tile is the
+    // box C x M/4; the scratch ring the same way over slots * gt transforms; the output as [nbatch * R][M], box C2 x R/4
     EncodeTiledFn enc = encode_tiled_fn();
     if (!enc) return fail("cuTensorMapEncodeTiled is not available from this driver");
-    CUtensorMap tm;
-    const cuuint64_t gdim[2] = {(cuuint64_t)2 << lr, (cuuint64_t)nbatch << lm};
-    const cuuint64_t gstr[1] = {(cuuint64_t)sizeof(cd) << lr};
-    const cuuint32_t box[2] = {(cuuint32_t)2 << (12 - lm), (cuuint32_t)(lm > 8 ? 256 : 1 << lm)};
-    const cuuint32_t estr[2] = {1, 1};
+    CUtensorMap tm[3];
     int promo = 12 - lm >= 4 ? 2 : 12 - lm >= 3 ? 1 : 0;      // rows of 256 / 128 / 64 bytes
     if (const char* e = getenv("FFTB200_FUSED_PROMO")) promo = atoi(e);
     const CUtensorMapL2promotion pr = promo >= 2 ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B : promo == 1 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B
                                                                                                    : CU_TENSOR_MAP_L2_PROMOTION_NONE;
-    const CUresult r = enc(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, (void*)in, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                           CU_TENSOR_MAP_SWIZZLE_NONE, pr, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled failed (%d)", (int)r);
+    for (int i = 0; i < 3; i++) {
+        const int lcols = i == 2 ? lm : lr, lrows = i == 2 ? lr : lm;          // row length / rows per transform (log2)
+        const long long ntr = i == 1 ? slots * gt : nbatch;
+        void* base = i == 0 ? (void*)in : i == 1 ? (void*)p->fscratch : (void*)out;
+        const cuuint64_t gdim[2] = {(cuuint64_t)2 << lcols, (cuuint64_t)ntr << lrows};
+        const cuuint64_t gstr[1] = {(cuuint64_t)sizeof(cd) << lcols};
+        const cuuint32_t box[2] = {(cuuint32_t)2 << (12 - lrows), (cuuint32_t)1 << (lrows - 2)};   // a quarter tile: 1024 elements
+        const cuuint32_t estr[2] = {1, 1};
+        const CUresult r = enc(&tm[i], CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, base, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                               CU_TENSOR_MAP_SWIZZLE_NONE, i == 0 ? pr : CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled failed (%d) for map %d", (int)r, i);
+    }
     FusedArgs fa;
-    fa.in = in; fa.out = out; fa.scratch = p->fscratch; fa.tab = p->tab; fa.acc = p->acc; fa.flags = p->fflags;
+    fa.scratch = p->fscratch; fa.tab = p->tab; fa.acc = p->acc; fa.flags = p->fflags;
     fa.nbatch = nbatch; fa.gt = (int)gt; fa.ngroups = (int)G; fa.lag = (int)lag; fa.slots = (int)slots;
     fa.inverse = inverse; fa.scale = 1.0 / (double)p->m;
     fa.debug = getenv("FFTB200_FUSED_DEBUG") ? atoi(getenv("FFTB200_FUSED_DEBUG")) : 0;
@@ -408,7 +414,7 @@ static int enqueue_fused(fftb200_plan* p, const Pass& ps, const cd* in, cd* out,
     fa.prof = nullptr;
 #ifdef FUSED_PROF
     static long long* d_prof = nullptr;
-    if (!d_prof) d_prof = (long long*)fftb200_malloc(sizeof(long long) * 32 * 1024);
+    if (!d_prof) d_prof = (long long*)fftb200_malloc(sizeof(long long) * 16 * 1024);
     fa.prof = d_prof;
 #endif
     const long long items = 2 * nbatch * tpt;
@@ -418,18 +424,19 @@ static int enqueue_fused(fftb200_plan* p, const Pass& ps, const cd* in, cd* out,
 #ifdef FUSED_PROF
     if (getenv("FFTB200_FUSED_PROF_PRINT")) {
         CU(cudaStreamSynchronize(p->stream));
-        std::vector<long long> h(32 * grid);
-        CU(cudaMemcpy(h.data(), fa.prof, sizeof(long long) * 32 * grid, cudaMemcpyDeviceToHost));
-        double e = 0, f = 0, tot = 0, tiles = 0, ph[12] = {0};
-        for (int i = 0; i < 2 * grid; i++) {
-            e += h[i * 16]; f += h[i * 16 + 1]; tot += h[i * 16 + 2]; tiles += h[i * 16 + 3];
-            for (int j = 0; j < 12; j++) ph[j] += h[i * 16 + 4 + j];
+        std::vector<long long> h(8 * grid);
+        CU(cudaMemcpy(h.data(), fa.prof, sizeof(long long) * 8 * grid, cudaMemcpyDeviceToHost));
+        double e = 0, f = 0, tot = 0, tiles = 0;
+        for (int i = 0; i < 2 * grid; i++) { e += h[i * 4]; f += h[i * 4 + 1]; tot += h[i * 4 + 2]; tiles += h[i * 4 + 3]; }
+        {
+            std::vector<long long> hm(8 * 3 * grid);
+            CU(cudaMemcpy(hm.data(), fa.prof + 8 * 1024, sizeof(long long) * 8 * 3 * grid, cudaMemcpyDeviceToHost));
+            double v[5] = {0, 0, 0, 0, 0};
+            for (int i = 0; i < 3 * grid; i++) for (int j = 0; j < 5; j++) v[j] += hm[i * 8 + j];
+            fprintf(stderr, "fused prof managers: per tile cycles: load latency %.0f, loaded->staged %.0f, store read-out + next load issue %.0f, publish %.0f\n",
+                    v[0] / v[4], v[1] / v[4], v[2] / v[4], v[3] / v[4]);
         }
-        fprintf(stderr, "fused prof phases per group-tile (all tiles): A: sp0 %.0f sync %.0f sp1 %.0f war+sync %.0f store %.0f signal %.0f | "
-                "B: sp0 %.0f sync %.0f mid+gatherL %.0f sync %.0f tw+bfly+store %.0f signal %.0f\n",
-                ph[0] / tiles, ph[1] / tiles, ph[2] / tiles, ph[3] / tiles, ph[4] / tiles, ph[5] / tiles, ph[6] / tiles, ph[7] / tiles,
-                ph[8] / tiles, ph[9] / tiles, ph[10] / tiles, ph[11] / tiles);
-        fprintf(stderr, "fused prof: per group-tile cycles: total %.0f, empty-wait %.0f, full-wait %.0f, busy %.0f (tiles/group %.1f)\n",
+        fprintf(stderr, "fused prof: per group-tile cycles: total %.0f, staged-wait %.0f, full-wait %.0f, busy %.0f (tiles/group %.1f)\n",
                 tot / tiles, e / tiles, f / tiles, (tot - e - f) / tiles, tiles / (2 * grid));
     }
 #endif

@@ -59,6 +59,45 @@ __global__ void __launch_bounds__(THREADS) twopass_kernel(double2* out, const do
     }
 }
 
+// mode 3: per-SM TMA (bulk async copy) throughput: NB ring buffers of 64 KB per CTA, one thread drives them.
+// what: 1 = loads only, 2 = stores only, 3 = load then store of every tile (copy through shared memory)
+__device__ __forceinline__ uint32_t s32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+template <int NB>
+__global__ void __launch_bounds__(128) tma_kernel(double2* out, const double2* in, long long ntiles, long long wrap, int what, long long wrap_out = 0, int spin = 0) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    double2* bufs = (double2*)smem;
+    uint64_t* full = (uint64_t*)(smem + (size_t)NB * TILE * 16);
+    if (threadIdx.x == 0) {
+        for (int b = 0; b < NB; b++) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(s32(&full[b])));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x >= NB) return;
+    // thread b drives buffer b (as the manager warps of the fused kernel do, here lanes of one warp)
+    const int b = threadIdx.x;
+    const long long mine = blockIdx.x < ntiles ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    int n = 0;
+    for (long long k = b; k < mine; k += NB, n++) {
+        const long long t = (blockIdx.x + k * gridDim.x) % wrap;
+        if (what & 1) {
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(s32(&full[b])), "r"(TILE * 16) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(s32(bufs + (size_t)b * TILE)),
+                         "l"(in + t * TILE), "r"(TILE * 16), "r"(s32(&full[b])) : "memory");
+            uint32_t ok = 0;
+            while (!ok) asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n" : "=r"(ok) : "r"(s32(&full[b])), "r"(n & 1) : "memory");
+        }
+        if (spin) { const long long t0 = clock64(); while (clock64() - t0 < spin) {} }   // stands for the compute time of a tile
+        if (what & 2) {
+            const long long to = wrap_out ? (blockIdx.x + k * gridDim.x) % wrap_out : t;
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(out + to * TILE), "r"(s32(bufs + (size_t)b * TILE)), "r"(TILE * 16) : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        }
+    }
+    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+
 int main(int argc, char** argv) {
     const int mode = argc > 1 ? atoi(argv[1]) : 0;
     const long long big_mb = 4096;
@@ -93,6 +132,30 @@ int main(int argc, char** argv) {
                 float ms = time([&] { if (h) twopass_kernel<true><<<grid, THREADS>>>(b, a, r, big_tiles, rt, lag); else twopass_kernel<false><<<grid, THREADS>>>(b, a, r, big_tiles, rt, lag); });
                 printf("mode2 twopass ring %d MB lag %d hint=%d: %.3f ms, strict %.0f GB/s (32 B/pt)\n", mb, lag, h, ms, 2.0 * (big_mb << 20) / ms * 1e-6);
             }
+    }
+    if (mode == 3 || mode == 9) {
+        CK(cudaFuncSetAttribute(tma_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * TILE * 16 + 64));
+        CK(cudaFuncSetAttribute(tma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * TILE * 16 + 64));
+        for (int l2 = 0; l2 < 2; l2++)
+            for (int what = 1; what <= 3; what++)
+                for (int nb = 2; nb <= 3; nb++) {
+                    const long long wrap = l2 ? (24ll << 20) / (TILE * 16) : big_tiles;
+                    float ms = time([&] { if (nb == 3) tma_kernel<3><<<sms, 128, 3 * TILE * 16 + 64>>>(b, a, big_tiles, wrap, what);
+                                          else tma_kernel<2><<<sms, 128, 2 * TILE * 16 + 64>>>(b, a, big_tiles, wrap, what); });
+                    const double bytes = (double)(big_mb << 20) * ((what & 1) + ((what >> 1) & 1));
+                    printf("mode3 tma %s %s bufs=%d: %.3f ms, %.0f GB/s total, %.1f B/clk/SM @1.9GHz\n", l2 ? "L2(24MB)" : "HBM(4GiB)",
+                           what == 1 ? "load " : what == 2 ? "store" : "copy ", nb, ms, bytes / ms * 1e-6, bytes / ms * 1e-6 / sms / 1.9);
+                }
+    }
+    if (mode == 4 || mode == 9) {
+        CK(cudaFuncSetAttribute(tma_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * TILE * 16 + 64));
+        const long long rw = (24ll << 20) / (TILE * 16);
+        for (int spin : {0, 2000, 4000, 6000}) {
+            float ms = time([&] { tma_kernel<3><<<sms, 128, 3 * TILE * 16 + 64>>>(r, a, big_tiles, big_tiles, 3, rw, spin); });
+            printf("mode4 tma copy HBM -> L2 ring (pass A shape), 3 bufs, compute %d cyc: %.3f ms\n", spin, ms);
+            ms = time([&] { tma_kernel<3><<<sms, 128, 3 * TILE * 16 + 64>>>(b, r, big_tiles, rw, 3, 0, spin); });
+            printf("mode4 tma copy L2 ring -> HBM (pass B shape), 3 bufs, compute %d cyc: %.3f ms\n", spin, ms);
+        }
     }
     return 0;
 }
