@@ -90,6 +90,9 @@ _SIGS = {
     "fftb200_timer_start": (C.c_int, [_vp]),
     "fftb200_timer_stop": (C.c_int, [_vp, C.POINTER(C.c_float)]),
     "fftb200_pointwise_mul": (C.c_int, [_vp, _vp, _vp, C.c_size_t]),
+    "fftb200_plan_create_partial": (C.c_int, [C.POINTER(_vp), _vp, C.c_int, C.c_int, C.c_int, C.c_double]),
+    "fftb200_permute_bac": (C.c_int, [_vp, _vp, C.c_longlong, C.c_longlong, C.c_longlong, _vp]),
+    "fftb200_plan_stream": (_vp, [_vp]),
     "fftb200_last_error": (C.c_char_p, []),
     # host-library helpers (not part of the reference API)
     "fftb200_engine_of": (_vp, [_vp]),
@@ -97,6 +100,7 @@ _SIGS = {
     "fftb200_host_twiddles": (_vp, [C.c_int]),
     "fftb200_host_chirp": (None, [_vp, C.c_int, C.c_int]),
     "fftb200_host_tables_release": (None, []),
+    "fftb200_host_twiddles_dist": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_int]),
     "fftb200_shard_range": (C.c_int, [C.c_longlong, C.c_int, C.c_int, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]),
 }
 EXPORTS = sorted(_SIGS)

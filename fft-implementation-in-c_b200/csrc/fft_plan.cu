@@ -206,6 +206,8 @@ struct fftb200_plan {
     int* fflags = nullptr;     // fused plans: per-group completion counters
     size_t fflags_count = 0;
     cd fdtw[3][16];            // fused plans: pass-B derived-twiddle constants (fft_fused.cuh: fused_twiddles)
+    cd* own_tab = nullptr;     // partial plans with a private (rank-specific) twiddle table
+    double scale = 0.0;        // 1/m, or the caller's value for partial plans of a distributed transform
     cd* work = nullptr;        // Bluestein / R2C: padded complex work array, m * batch
     cd* chirp = nullptr;       // Bluestein: n entries
     cd* fb = nullptr;          // Bluestein: FFT_m of the wrapped chirp
@@ -408,7 +410,7 @@ static int enqueue_fused(fftb200_plan* p, const Pass& ps, const cd* in, cd* out,
     FusedArgs fa;
     fa.scratch = p->fscratch; fa.tab = p->tab; fa.acc = p->acc; fa.flags = p->fflags;
     fa.nbatch = nbatch; fa.gt = (int)gt; fa.ngroups = (int)G; fa.lag = (int)lag; fa.slots = (int)slots;
-    fa.inverse = inverse; fa.scale = 1.0 / (double)p->m;
+    fa.inverse = inverse; fa.scale = p->scale;
     fa.debug = getenv("FFTB200_FUSED_DEBUG") ? atoi(getenv("FFTB200_FUSED_DEBUG")) : 0;
     memcpy(fa.dtw, p->fdtw, sizeof(fa.dtw));
     fa.prof = nullptr;
@@ -488,7 +490,7 @@ static int enqueue_c2c_range(fftb200_plan* p, const cd* in, cd* out, int inverse
             PipeArgs pa;
             pa.in = in; pa.out = out; pa.tab = p->acc;
             pa.ntiles = ntiles; pa.batch = nbatch;
-            pa.inverse = inverse; pa.scale = 1.0 / (double)p->m;
+            pa.inverse = inverse; pa.scale = p->scale;
             launch_pipe(ps.log_p, pa, grid, p->stream);
             continue;
         }
@@ -498,7 +500,7 @@ static int enqueue_c2c_range(fftb200_plan* p, const cd* in, cd* out, int inverse
         a.in = src; a.out = dst; a.tab = p->tab;
         a.ntiles = ntiles; a.batch = nbatch;
         a.log_n = p->log_n; a.log_m = ps.log_m;
-        a.inverse = inverse; a.scale = 1.0 / (double)p->m; a.final_pass = ps.final_pass;
+        a.inverse = inverse; a.scale = p->scale; a.final_pass = ps.final_pass;
         ps.k->launch(a, grid, p->stream);
     }
     CU(cudaGetLastError());
@@ -563,6 +565,7 @@ extern "C" int fftb200_plan_create(fftb200_plan** out, const fftb200_plan_desc* 
             if (!d->chirp) { rc = fail("plan_create: Bluestein needs a host chirp table"); break; }
         } else { rc = fail("plan_create: unknown kind %d", d->kind); break; }
         p->log_n = ilog2(p->m);
+        p->scale = 1.0 / (double)p->m;
         if ((rc = cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking)) != 0) { rc = fail("cudaStreamCreate failed"); break; }
         if (cudaStreamCreateWithFlags(&p->s_up, cudaStreamNonBlocking) != cudaSuccess ||
             cudaStreamCreateWithFlags(&p->s_down, cudaStreamNonBlocking) != cudaSuccess) { rc = fail("cudaStreamCreate failed"); break; }
@@ -613,6 +616,119 @@ extern "C" int fftb200_plan_create(fftb200_plan** out, const fftb200_plan_desc* 
     *out = p;
     return 0;
 }
+
+// ---------------------------------------------------------------------------------------------
+// partial plans: stages [first_stage, first_stage + nstages) of the size-n Stockham transform
+// ---------------------------------------------------------------------------------------------
+// Building block of the distributed transform (N = R * M over G GPUs): between two all-to-all
+// exchanges every GPU runs the first log2 M stages of one local array and, later, the last log2 R stages of
+// another, the latter with a rank-specific table holding the reference's late-stage twiddles T[s][k + M q] for
+// the k range the rank owns (host/ref_twiddle.c: fftb200_host_twiddles_dist). State before the first executed
+// stage is the Stockham layout idx = c + (n / 2^first_stage) * k; the output is the layout after the last
+// executed stage (natural order when the plan reaches stage log2 n).
+static int split_partial(int cnt, std::vector<int>* v) {
+    for (int np = 1; np <= 4; np++) {
+        if (cnt < 6 * np || cnt > 9 * np) continue;
+        const int base = cnt / np, extra = cnt % np;
+        for (int i = 0; i < np; i++) v->push_back(base + (i < extra ? 1 : 0));
+        return 0;
+    }
+    return -1;
+}
+
+extern "C" int fftb200_plan_create_partial(fftb200_plan** out, const fftb200_plan_desc* d, int first_stage, int nstages,
+                                           int private_table, double inverse_scale) {
+    if (!out || !d) return fail("plan_create_partial: null argument");
+    *out = nullptr;
+    if (d->n <= 0 || (d->n & (d->n - 1)) || d->batch <= 0) return fail("plan_create_partial: n must be a power of two, batch positive");
+    if (d->direction != -1 && d->direction != 1) return fail("plan_create_partial: direction must be -1 or +1");
+    const int L = ilog2(d->n);
+    if (first_stage < 0 || nstages < 1 || first_stage + nstages > L) return fail("plan_create_partial: bad stage range");
+    std::vector<int> sizes;
+    if (split_partial(nstages, &sizes) != 0) return fail("plan_create_partial: %d stages cannot be split into passes of 6..9", nstages);
+    DeviceState* ds;
+    if (cur_device(&ds) != 0) return -1;
+    fftb200_plan* p = new fftb200_plan();
+    p->device = fftb200_get_device();
+    p->n = d->n; p->batch = d->batch; p->dir = d->direction; p->kind = FFTB200_C2C;
+    p->m = d->n; p->log_n = L; p->scale = inverse_scale;
+    int rc = 0;
+    do {
+        if (cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking) != cudaSuccess ||
+            cudaStreamCreateWithFlags(&p->s_up, cudaStreamNonBlocking) != cudaSuccess ||
+            cudaStreamCreateWithFlags(&p->s_down, cudaStreamNonBlocking) != cudaSuccess) { rc = fail("cudaStreamCreate failed"); break; }
+        if (cudaEventCreate(&p->ev0) != cudaSuccess || cudaEventCreate(&p->ev1) != cudaSuccess) { rc = fail("cudaEventCreate failed"); break; }
+        const int need_n = 1 << (first_stage + nstages);
+        if (private_table) {
+            if (!d->twiddles || d->table_n < need_n) { rc = fail("plan_create_partial: private table too small"); break; }
+            const size_t bytes = sizeof(cd) * (size_t)(need_n - 1);
+            if (cudaMalloc(&p->own_tab, bytes) != cudaSuccess) { rc = fail("cudaMalloc(%zu) for the private table failed", bytes); cudaGetLastError(); break; }
+            if (cudaMemcpy(p->own_tab, d->twiddles, bytes, cudaMemcpyHostToDevice) != cudaSuccess ||
+                cudaStreamSynchronize(cudaStreamLegacy) != cudaSuccess) { rc = fail("private table upload failed"); break; }
+            p->tab = p->own_tab;
+        } else if ((rc = upload_table(p, ds, d, need_n)) != 0) break;
+        char head[96];
+        snprintf(head, sizeof(head), "partial n=%d b=%d dir=%d stages [%d,%d): ", d->n, d->batch, d->direction, first_stage, first_stage + nstages);
+        p->desc = head;
+        const int np = (int)sizes.size();
+        int log_m = first_stage;
+        for (int i = 0; i < np && rc == 0; i++) {
+            Pass ps;
+            const int lp = sizes[i];
+            ps.log_p = lp;
+            const bool last = (log_m + lp == L);
+            const int mode = last ? MODE_LAST : MODE_STRIDED;
+            ps.k = find_kernel(mode, lp, mode == MODE_STRIDED ? (log_m == 0) : 0);
+            if (!ps.k) { rc = fail("no kernel variant for mode %d, 2^%d points", mode, lp); break; }
+            ps.log_m = log_m;
+            ps.nt = 0; ps.shift = 0;
+            if (mode == MODE_STRIDED) {
+                const int log_rest = L - log_m - lp;
+                if (log_rest < ps.k->logc) { rc = fail("pass split leaves too few columns"); break; }
+                ps.shift = log_rest - ps.k->logc + log_m;
+            } else {
+                if (log_m < ps.k->logc) { rc = fail("last pass too wide"); break; }
+                ps.shift = log_m - ps.k->logc;
+            }
+            ps.src = (i == 0) ? BUF_IN : (((np - 1 - (i - 1)) % 2 == 0) ? BUF_OUT : BUF_SCRATCH);
+            ps.dst = ((np - 1 - i) % 2 == 0) ? BUF_OUT : BUF_SCRATCH;
+            ps.final_pass = (i == np - 1);
+            if (cudaFuncSetAttribute(ps.k->func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ps.k->smem) != cudaSuccess) { rc = fail("cudaFuncSetAttribute failed"); break; }
+            int occ = 0;
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ps.k->func, ps.k->threads, ps.k->smem) != cudaSuccess || occ < 1) { rc = fail("kernel variant does not fit on an SM"); break; }
+            ps.grid_max = ds->sms * occ;
+            p->passes.push_back(ps);
+            char b[64];
+            snprintf(b, sizeof(b), "%s%c%d(occ%d)", i ? "+" : "", mode == MODE_LAST ? 'L' : (log_m == 0 ? 'F' : 'M'), lp, occ);
+            p->desc += b;
+            log_m += lp;
+        }
+        p->launches = (int)p->passes.size();
+    } while (0);
+    if (rc != 0) { fftb200_plan_destroy(p); return -1; }
+    *out = p;
+    return 0;
+}
+
+// dst[b][a][c] = src[a][b][c] over complex elements, c contiguous: the local half of the block transposes around
+// the all-to-all exchanges of the distributed transform
+__global__ void permute_bac_kernel(cd* __restrict__ dst, const cd* __restrict__ src, long long A, long long B, long long C) {
+    const long long total = A * B * C, stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+        const long long c = i % C, ab = i / C, a = ab % A, b = ab / A;   // i indexes dst = [b][a][c]
+        dst[i] = src[(a * B + b) * C + c];
+    }
+}
+extern "C" int fftb200_permute_bac(void* dst, const void* src, long long A, long long B, long long C, void* stream) {
+    if (!dst || !src || A < 1 || B < 1 || C < 1 || dst == src) return fail("permute_bac: bad argument");
+    const long long total = A * B * C;
+    long long blocks = (total + 255) / 256;
+    if (blocks > 148 * 32) blocks = 148 * 32;
+    permute_bac_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((cd*)dst, (const cd*)src, A, B, C);
+    CU(cudaGetLastError());
+    return 0;
+}
+extern "C" void* fftb200_plan_stream(fftb200_plan* p) { return p ? (void*)p->stream : nullptr; }
 
 static unsigned grid_for(size_t total) {
     const size_t b = (total + 255) / 256;
@@ -716,6 +832,7 @@ extern "C" void fftb200_plan_destroy(fftb200_plan* p) {
     if (p->scratch) cudaFree(p->scratch);
     if (p->fscratch) cudaFree(p->fscratch);
     if (p->fflags) cudaFree(p->fflags);
+    if (p->own_tab) cudaFree(p->own_tab);
     if (p->work) cudaFree(p->work);
     if (p->chirp) cudaFree(p->chirp);
     if (p->fb) cudaFree(p->fb);

@@ -137,6 +137,39 @@ const double* fftb200_host_twiddles(int n) {
     return r;
 }
 
+/* Rank-specific table for the tail plan of a distributed transform of 2^log_total points over 2^log_world ranks
+ * with M = 2^log_m points in the first pass: laid out like the table of a 2^(log_total - log_world)-point
+ * transform, but entry (stage s', j' = k_loc + M' q), M' = M / world, holds the reference's
+ * T[s' + log_world][k_loc + rank * M' + M q] for every stage s' > log_m - log_world. Earlier stages are not read
+ * by the tail plan and are left zero. The recurrence is serial per stage, so each rank walks all of it (about
+ * 2^log_total steps in total) and keeps its 1/world share. Returns 0, -1 on bad arguments. */
+int fftb200_host_twiddles_dist(double* out, int log_total, int log_world, int rank, int log_m) {
+    if (!out || log_total < 2 || log_total > 30 || log_world < 0 || log_m < log_world || log_m >= log_total ||
+        rank < 0 || rank >= (1 << log_world)) return -1;
+    const int log_local = log_total - log_world;
+    const long long mloc = 1LL << (log_m - log_world), m = 1LL << log_m, k0 = (long long)rank * mloc;
+    memset(out, 0, sizeof(double) * 2 * (size_t)((1LL << log_local) - 1));
+    for (int s = log_m + 1; s <= log_total; s++) {
+        const long long half = 1LL << (s - 1);
+        double* t = out + 2 * ((size_t)(1LL << (s - log_world - 1)) - 1);
+        double mr, mi, wr = 1.0, wi = 0.0;
+        stage_root((int)(2 * half), &mr, &mi);   /* 2 * half <= 2^30 fits an int */
+        for (long long j = 0; j < half; j++) {
+            const long long k = j & (m - 1);
+            if (k >= k0 && k < k0 + mloc) {
+                const long long jj = (k - k0) + mloc * (j >> log_m);
+                t[2 * jj] = wr;
+                t[2 * jj + 1] = wi;
+            }
+            const double p_im_mi = wi * mi, p_im_mr = wi * mr;
+            const double nr = fma(wr, mr, -p_im_mi);
+            const double ni = fma(wr, mi, p_im_mr);
+            wr = nr; wi = ni;
+        }
+    }
+    return 0;
+}
+
 void fftb200_host_tables_release(void) {
     pthread_mutex_lock(&g_mu);
     for (int i = 0; i < g_nold; i++) free(g_old[i]);

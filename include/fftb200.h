@@ -84,6 +84,18 @@ void fftb200_plan_destroy(fftb200_plan* plan);
 int fftb200_plan_launches(const fftb200_plan* plan);     /* kernel launches per execution         */
 const char* fftb200_plan_describe(const fftb200_plan* plan); /* e.g. "c2c n=4096 b=65536: C12"    */
 
+/* ---- pieces of the distributed transform (one process per GPU, exchanges done by the caller) ----
+ * A partial plan runs stages [first_stage, first_stage + nstages) of the size-n transform on the Stockham layout
+ * idx = c + (n >> first_stage) * k; desc->twiddles must cover stages up to first_stage + nstages (table_n >= 2^that).
+ * private_table != 0 uploads the table for this plan only (rank-specific late-stage tables, see
+ * fftb200_host_twiddles_dist in fftb200_ext.h). inverse_scale is applied by the pass that ends the plan when
+ * direction = +1 (pass 1.0 for the head plan and 1/N for the tail plan of an inverse transform). */
+int fftb200_plan_create_partial(fftb200_plan** out, const fftb200_plan_desc* desc, int first_stage, int nstages,
+                                int private_table, double inverse_scale);
+/* dst[b][a][c] = src[a][b][c], complex elements, c contiguous; enqueued on `stream` (a cudaStream_t, may be NULL). */
+int fftb200_permute_bac(void* d_dst, const void* d_src, long long A, long long B, long long C, void* stream);
+void* fftb200_plan_stream(fftb200_plan* plan);   /* the plan's cudaStream_t */
+
 /* ---- timing on the plan's stream (CUDA events) ---- */
 int fftb200_timer_start(fftb200_plan* plan);
 int fftb200_timer_stop(fftb200_plan* plan, float* elapsed_ms);   /* synchronises on the stop event */

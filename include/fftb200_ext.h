@@ -27,5 +27,8 @@ int fftb200_shard_range(long long batch, int world, int rank, long long* first, 
 const double* fftb200_host_twiddles(int n);           /* n - 1 complex, stage s entry j at 2^(s-1) - 1 + j */
 void fftb200_host_chirp(double* out, int n, int dir); /* n complex */
 void fftb200_host_tables_release(void);
+/* Late-stage reference twiddles owned by `rank` in a distributed transform (see host/ref_twiddle.c); out holds
+ * 2^(log_total - log_world) - 1 complex numbers. */
+int fftb200_host_twiddles_dist(double* out, int log_total, int log_world, int rank, int log_m);
 
 #endif /* FFTB200_EXT_H */

@@ -259,3 +259,44 @@ def test_config3_linearity_at_2_24(gpu):
     err = float(torch.linalg.vector_norm(y[2] - (2 * y[0] + 3 * y[1])) / torch.linalg.vector_norm(y[2]))
     assert err <= TOL
     L.fft_gpu_destroy_plan(plan)
+
+
+# ---- distributed transform (fft-implementation-in-c_b200/dist.py): partial plans + rank tables on one GPU, ranks on several ----
+def _dist_module():
+    import importlib.util
+    import fftb200_loader
+    spec = importlib.util.spec_from_file_location("fft_b200_dist", os.path.join(fftb200_loader.PKG_DIR, "dist.py"))
+    D = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(D)
+    return D
+
+
+@pytest.mark.parametrize("log_n,direction", [(20, -1), (21, 1), (22, -1), (24, -1)])
+def test_distributed_plan_world_1_matches_the_oracle(gpu, port, O, log_n, direction):
+    """World size 1 runs the same head / tail partial plans and rank table as any rank of a multi-GPU job."""
+    import torch
+    D = _dist_module()
+    n = 1 << log_n
+    plan = D.DistFFT(n, 1, 0, lambda *a: D.CudaBackend(gpu, *a), direction=direction)
+    x = port.fill(45, 0, n)
+    y = plan.execute(torch.from_numpy(x).cuda())
+    torch.cuda.synchronize()
+    assert O.rel_l2(y.cpu().numpy(), port.fft(x, direction)) <= TOL
+    plan.close()
+
+
+def test_distributed_two_ranks_match_the_single_gpu_plan(gpu):
+    """Two ranks over NCCL (needs two GPUs; the single-GPU box of the round-end run skips it)."""
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29533", os.path.join(root, "tools", "dist_check.py"), "22", "24", "--inverse", "--notime"],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    import json
+    errs = [json.loads(l)["rel_l2_vs_single_gpu_plan"] for l in r.stdout.replace("}{", "}\n{").splitlines() if l.startswith("{")]
+    assert len(errs) == 8 and max(errs) <= TOL
