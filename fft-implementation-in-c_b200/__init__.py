@@ -93,6 +93,13 @@ _SIGS = {
     "fftb200_plan_create_partial": (C.c_int, [C.POINTER(_vp), _vp, C.c_int, C.c_int, C.c_int, C.c_double]),
     "fftb200_permute_bac": (C.c_int, [_vp, _vp, C.c_longlong, C.c_longlong, C.c_longlong, _vp]),
     "fftb200_plan_stream": (_vp, [_vp]),
+    "fftb200_peers_create": (C.c_int, [C.POINTER(_vp), C.POINTER(_vp), C.c_int, C.c_int]),
+    "fftb200_peers_destroy": (None, [_vp]),
+    "fftb200_plan_set_peer_output": (C.c_int, [_vp, _vp, C.c_int, C.c_int]),
+    "fftb200_push_columns": (C.c_int, [_vp, _vp, _vp, C.c_longlong, C.c_int]),
+    "fftb200_ipc_export": (C.c_int, [_vp, _vp]),
+    "fftb200_ipc_open": (_vp, [_vp]),
+    "fftb200_ipc_close": (C.c_int, [_vp]),
     "fftb200_last_error": (C.c_char_p, []),
     # host-library helpers (not part of the reference API)
     "fftb200_engine_of": (_vp, [_vp]),

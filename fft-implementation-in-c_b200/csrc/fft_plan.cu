@@ -207,6 +207,8 @@ struct fftb200_plan {
     size_t fflags_count = 0;
     cd fdtw[3][16];            // fused plans: pass-B derived-twiddle constants (fft_fused.cuh: fused_twiddles)
     cd* own_tab = nullptr;     // partial plans with a private (rank-specific) twiddle table
+    cd** peers = nullptr;      // partial plans whose last pass stores into the peers' exchange buffers (device array of G pointers)
+    int peer_lw = 0, peer_lrows = 0, peer_lg = 0, peer_me = 0;
     double scale = 0.0;        // 1/m, or the caller's value for partial plans of a distributed transform
     cd* work = nullptr;        // Bluestein / R2C: padded complex work array, m * batch
     cd* chirp = nullptr;       // Bluestein: n entries
@@ -501,6 +503,8 @@ static int enqueue_c2c_range(fftb200_plan* p, const cd* in, cd* out, int inverse
         a.ntiles = ntiles; a.batch = nbatch;
         a.log_n = p->log_n; a.log_m = ps.log_m;
         a.inverse = inverse; a.scale = p->scale; a.final_pass = ps.final_pass;
+        a.peers = (ps.final_pass && p->peers) ? p->peers : nullptr;
+        a.peer_lw = p->peer_lw; a.peer_lrows = p->peer_lrows; a.peer_lg = p->peer_lg; a.peer_me = p->peer_me;
         ps.k->launch(a, grid, p->stream);
     }
     CU(cudaGetLastError());
@@ -729,6 +733,75 @@ extern "C" int fftb200_permute_bac(void* dst, const void* src, long long A, long
     return 0;
 }
 extern "C" void* fftb200_plan_stream(fftb200_plan* p) { return p ? (void*)p->stream : nullptr; }
+
+// Peer tables: device arrays of the 2^log_world base pointers of one exchange buffer on every rank (own buffer +
+// IPC-opened peers), as seen from THIS process.
+struct fftb200_peers {
+    cd** d_bases = nullptr;
+    int log_world = 0, rank = 0;
+};
+extern "C" int fftb200_peers_create(fftb200_peers** out, void* const* bases, int log_world, int rank) {
+    if (!out || !bases || log_world < 0 || log_world > 6 || rank < 0 || rank >= (1 << log_world)) return fail("peers_create: bad argument");
+    fftb200_peers* t = new fftb200_peers();
+    t->log_world = log_world; t->rank = rank;
+    if (cudaMalloc(&t->d_bases, sizeof(cd*) << log_world) != cudaSuccess ||
+        cudaMemcpy(t->d_bases, bases, sizeof(cd*) << log_world, cudaMemcpyHostToDevice) != cudaSuccess) {
+        cudaGetLastError(); delete t; return fail("peers_create: device table failed");
+    }
+    *out = t;
+    return 0;
+}
+extern "C" void fftb200_peers_destroy(fftb200_peers* t) {
+    if (!t) return;
+    if (t->d_bases) cudaFree(t->d_bases);
+    delete t;
+}
+// The last pass of a partial plan writes into the exchange buffers of all ranks (fft_tile.cuh: peer_ptr).
+extern "C" int fftb200_plan_set_peer_output(fftb200_plan* p, const fftb200_peers* t, int log_width, int log_rows_per_rank) {
+    if (!p || !t) return fail("set_peer_output: null argument");
+    p->peers = t->d_bases;   // borrowed: the table must outlive the plan's executions
+    p->peer_lw = log_width; p->peer_lrows = log_rows_per_rank; p->peer_lg = t->log_world; p->peer_me = t->rank;
+    return 0;
+}
+
+// dst_peer[g][(me * rows + t) * W + c] = src[t * (W << log_world) + g * W + c]: the first exchange (T0) as one kernel
+// that pushes the rank's rows, split by destination column block, straight into the peers' buffers
+__global__ void push_columns_kernel(cd* const* peers, const cd* __restrict__ src, long long rows, int lw, int lg, int me) {
+    const long long total = rows << (lw + lg), stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+        const long long c = i & ((1LL << lw) - 1), g = (i >> lw) & ((1LL << lg) - 1), t = i >> (lw + lg);
+        peers[g][(((long long)me * rows + t) << lw) + c] = src[i];
+    }
+}
+extern "C" int fftb200_push_columns(const fftb200_peers* t, void* stream, const void* src, long long rows, int log_width) {
+    if (!t || !src || rows < 1) return fail("push_columns: bad argument");
+    const long long total = rows << (log_width + t->log_world);
+    long long blocks = (total + 255) / 256;
+    if (blocks > 148 * 32) blocks = 148 * 32;
+    push_columns_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(t->d_bases, (const cd*)src, rows, log_width, t->log_world, t->rank);
+    CU(cudaGetLastError());
+    return 0;
+}
+
+// CUDA IPC: one process per GPU, so peers' exchange buffers are mapped through handles exchanged by the caller
+extern "C" int fftb200_ipc_export(void* dptr, void* handle64) {
+    if (!dptr || !handle64) return fail("ipc_export: null argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size");
+    CU(cudaIpcGetMemHandle((cudaIpcMemHandle_t*)handle64, dptr));
+    return 0;
+}
+extern "C" void* fftb200_ipc_open(const void* handle64) {
+    void* p = nullptr;
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, sizeof(h));
+    cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) { fail("cudaIpcOpenMemHandle: %s", cudaGetErrorString(e)); cudaGetLastError(); return nullptr; }
+    return p;
+}
+extern "C" int fftb200_ipc_close(void* p) {
+    if (p) CU(cudaIpcCloseMemHandle(p));
+    return 0;
+}
 
 static unsigned grid_for(size_t total) {
     const size_t b = (total + 255) / 256;

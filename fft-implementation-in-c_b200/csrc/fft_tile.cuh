@@ -39,7 +39,20 @@ struct TileArgs {
     int inverse;          // 0 forward, 1 inverse (conjugate in, conjugate out, scale)
     double scale;         // applied on the final store of the last pass when inverse
     int final_pass;       // this launch writes the user-visible result
+    // Distributed transform: the last pass of a partial plan stores straight into the peers' exchange buffers
+    // (P2P over NVLink) in the layout the next local pass wants, so the all-to-all is fused into the kernel.
+    // Output index idx = row * W + col (W = 2^peer_lw) goes to rank row >> peer_lrows at
+    // ((row & (2^peer_lrows - 1)) << (peer_lw + peer_lg)) + (peer_me << peer_lw) + col. peers == nullptr: local.
+    cd* const* peers;
+    int peer_lw, peer_lrows, peer_lg, peer_me;
 };
+
+__device__ __forceinline__ cd* peer_ptr(const TileArgs& a, long long idx) {
+    const long long row = idx >> a.peer_lw, col = idx & ((1LL << a.peer_lw) - 1);
+    const int dest = (int)(row >> a.peer_lrows);
+    const long long rloc = row & ((1LL << a.peer_lrows) - 1);
+    return a.peers[dest] + ((rloc << (a.peer_lw + a.peer_lg)) + ((long long)a.peer_me << a.peer_lw) + col);
+}
 
 // ---------------------------------------------------------------------------------------------
 // arithmetic
@@ -238,13 +251,15 @@ __device__ __forceinline__ void subpass(cd (&v)[C::E], cd* __restrict__ sm, cons
 #pragma unroll
         for (int b = 0; b < NB; b++) {
             const int u = ub[b];
-            cd* p = a.out + cx.out_base + (u & CM) + (long long)(u >> C::LOGC) * cx.out_rs;
+            const long long o = cx.out_base + (u & CM) + (long long)(u >> C::LOGC) * cx.out_rs;
+            cd* p = a.out + o;
             const long long step = (long long)(C::NP >> (LR + C::LOGC)) * cx.out_rs;
 #pragma unroll
             for (int q = 0; q < R; q++) {
                 cd x = v[b * R + q];
                 if (conj_out) { x.x *= sc; x.y *= -sc; }
-                if (cx.valid) p[q * step] = x;
+                if (a.peers) *peer_ptr(a, o + q * step) = x;
+                else if (cx.valid) p[q * step] = x;
             }
         }
     } else {

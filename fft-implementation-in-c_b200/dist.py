@@ -12,12 +12,17 @@ the reference's result (late-stage twiddles come from the reference recurrence, 
   T2      all-to-all: rank h gets q in [h R/G, (h+1) R/G) for every k                 -> X_h[q_loc][k] = X[k + M q]
   output  natural order, block-distributed like the input
 
-Each exchange is one NCCL all_to_all_single over NVLink (torch.distributed is the plumbing) plus one local block
-permute (fftb200_permute_bac) that makes the chunks contiguous; message shape per ordered GPU pair: N / G^2
-complex doubles (256 MiB at N = 2^30, G = 8). The local passes are the engine's Stockham tile kernels through the
-C ABI (fftb200_plan_create_partial). `DistFFT` is written against a small backend interface so that the same
-index algebra runs on CPU tensors with the gloo backend (tests/test_dist_gloo.py; numpy stands in for the
-kernels there, the CUDA backend is the product).
+Message shape per ordered GPU pair and exchange: N / G^2 complex doubles (256 MiB at N = 2^30, G = 8). Two drivers:
+
+  DistFFTP2P (the product)  the exchanges are FUSED into the kernels over NVSwitch peer memory: T0 is one push kernel,
+      T1 / T2 are the final scatter of the last head / tail pass, which stores straight into the peers' exchange
+      buffers (CUDA IPC mappings) in the layout the next local pass wants (csrc/fft_tile.cuh: peer_ptr). No NCCL
+      data movement and no separate transposes; NCCL only carries the three barriers between the phases.
+  DistFFT (baseline, and the CPU-testable statement of the algebra)  each exchange is one NCCL all_to_all_single
+      plus one local block permute (fftb200_permute_bac). It is written against a small backend interface so that
+      the same index algebra runs on CPU tensors with the gloo backend (tests/test_dist_gloo.py; numpy stands in
+      for the kernels there).
+The local passes are the engine's Stockham tile kernels through the C ABI (fftb200_plan_create_partial).
 """
 import ctypes as C
 import math
@@ -155,3 +160,123 @@ class DistFFT:
 
     def close(self):
         self.be.close()
+
+
+class _DevBuf:
+    """A cudaMalloc'ed complex128 buffer (fftb200_malloc) exposed to torch through __cuda_array_interface__."""
+
+    def __init__(self, lib, n):
+        self.lib, self.n = lib, n
+        self.ptr = lib.fftb200_malloc(16 * n)
+        if not self.ptr:
+            raise MemoryError(lib.fftb200_last_error().decode())
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<c16", "data": (self.ptr, False), "version": 2}
+
+    def tensor(self):
+        import torch
+        return torch.as_tensor(self, device="cuda")
+
+    def free(self):
+        if self.ptr:
+            self.lib.fftb200_free(self.ptr)
+            self.ptr = None
+
+
+class DistFFTP2P:
+    """Distributed transform with the exchanges fused into the kernels (P2P stores over NVLink / NVSwitch).
+
+    plan = DistFFTP2P(F, n_total, world, rank, direction); y = plan.execute(x_local)
+    y is a view of a buffer owned by the plan (natural order, this rank's block); it is overwritten by the next execute.
+    """
+
+    def __init__(self, F, n_total, world, rank, direction=-1, log_m=None, group=None):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist, self.F, self.group = torch, dist, F, group
+        L = F.lib
+        lt, lw = int(math.log2(n_total)), int(math.log2(world))
+        if (1 << lt) != n_total or (1 << lw) != world:
+            raise ValueError("n_total and world must be powers of two")
+        self.n, self.world, self.rank = n_total, world, rank
+        self.log_m = choose_split(lt, lw) if log_m is None else log_m
+        self.M, self.R = 1 << self.log_m, 1 << (lt - self.log_m)
+        self.be = CudaBackend(F, n_total, world, rank, self.log_m, direction)   # head / tail partial plans + streams
+        nloc = n_total // world
+        self.e0, self.e1, self.e2 = _DevBuf(L, nloc), _DevBuf(L, nloc), _DevBuf(L, nloc)
+        # exchange the IPC handles of e0 (receives T0 and T2) and e2 (receives T1)
+        hs = torch.zeros(2, 64, dtype=torch.uint8)
+        for i, b in enumerate((self.e0, self.e2)):
+            buf = (C.c_ubyte * 64)()
+            if L.fftb200_ipc_export(b.ptr, buf) != 0:
+                raise RuntimeError(L.fftb200_last_error().decode())
+            hs[i] = torch.frombuffer(bytearray(buf), dtype=torch.uint8)
+        allh = [torch.zeros(2, 64, dtype=torch.uint8, device="cuda") for _ in range(world)]
+        if world > 1:
+            dist.all_gather(allh, hs.cuda(), group=group)
+        else:
+            allh[0] = hs.cuda()
+        self._mapped = []
+        self.peers = []
+        for i, own in enumerate((self.e0, self.e2)):
+            bases = (C.c_void_p * world)()
+            for g in range(world):
+                if g == rank:
+                    bases[g] = own.ptr
+                else:
+                    h = bytes(allh[g][i].cpu().numpy().tobytes())
+                    p = L.fftb200_ipc_open(h)
+                    if not p:
+                        raise RuntimeError("ipc_open: " + L.fftb200_last_error().decode())
+                    self._mapped.append(p)
+                    bases[g] = p
+            t = C.c_void_p()
+            if L.fftb200_peers_create(C.byref(t), bases, lw, rank) != 0:
+                raise RuntimeError(L.fftb200_last_error().decode())
+            self.peers.append(t)
+        Ml, Rl = self.M // world, self.R // world
+        self.lml, self.lrl = int(math.log2(Ml)), int(math.log2(Rl))
+        # head output [k][r_loc] -> rank k / Ml, B[k_loc][rank * Rl + r_loc];  tail output [q][k_loc] -> rank q / Rl, X[q_loc][rank * Ml + k_loc]
+        if L.fftb200_plan_set_peer_output(self.be.head, self.peers[1], self.lrl, self.lml) != 0 or \
+           L.fftb200_plan_set_peer_output(self.be.tail, self.peers[0], self.lml, self.lrl) != 0:
+            raise RuntimeError(L.fftb200_last_error().decode())
+        self._tok = torch.zeros(1, device="cuda")
+        self.out = self.e0.tensor()
+
+    def _barrier(self):
+        if self.world > 1:
+            self.dist.all_reduce(self._tok, group=self.group)   # stream-ordered: completes when every rank's earlier kernels have
+
+    def execute(self, x):
+        L, be = self.F.lib, self.be
+        Ml = self.M // self.world
+        with be.stream():
+            self._barrier()                                                       # peers are done with the previous result
+            if L.fftb200_push_columns(self.peers[0], be.s_head.cuda_stream, x.data_ptr(), Ml, self.lrl) != 0:   # T0
+                raise RuntimeError(L.fftb200_last_error().decode())
+            self._barrier()
+            if L.fftb200_plan_exec_async(be.head, self.e0.ptr, self.e1.ptr) != 0:  # head, last pass stores into the peers' e2 (T1)
+                raise RuntimeError(L.fftb200_last_error().decode())
+            self._barrier()
+            ev = self.torch.cuda.Event()
+            ev.record(be.s_head)
+            be.s_tail.wait_event(ev)
+            if L.fftb200_plan_exec_async(be.tail, self.e2.ptr, self.e1.ptr) != 0:  # tail, last pass stores into the peers' e0 (T2)
+                raise RuntimeError(L.fftb200_last_error().decode())
+            ev2 = self.torch.cuda.Event()
+            ev2.record(be.s_tail)
+            be.s_head.wait_event(ev2)
+            self._barrier()
+        return self.out
+
+    def close(self):
+        L = self.F.lib
+        self.torch.cuda.synchronize()
+        if self.world > 1:
+            self.dist.barrier(group=self.group)
+        self.be.close()
+        for t in self.peers:
+            L.fftb200_peers_destroy(t)
+        for p in self._mapped:
+            L.fftb200_ipc_close(p)
+        for b in (self.e0, self.e1, self.e2):
+            b.free()

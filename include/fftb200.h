@@ -95,6 +95,23 @@ int fftb200_plan_create_partial(fftb200_plan** out, const fftb200_plan_desc* des
 /* dst[b][a][c] = src[a][b][c], complex elements, c contiguous; enqueued on `stream` (a cudaStream_t, may be NULL). */
 int fftb200_permute_bac(void* d_dst, const void* d_src, long long A, long long B, long long C, void* stream);
 void* fftb200_plan_stream(fftb200_plan* plan);   /* the plan's cudaStream_t */
+/* Fused exchange. A peer table holds the base pointers of one exchange buffer on all 2^log_world ranks as seen from
+ * this process (own buffer and IPC-opened peers). With fftb200_plan_set_peer_output the last pass of a partial plan
+ * stores over NVLink peer memory instead of into d_out: output index row * 2^log_width + col goes to rank
+ * row >> log_rows_per_rank, element ((row mod 2^log_rows_per_rank) << (log_width + log_world)) + (rank << log_width) + col,
+ * i.e. rows are split by destination and interleaved by source - the all-to-all and the block transpose in one.
+ * The table is borrowed by the plan and must outlive its executions. */
+typedef struct fftb200_peers fftb200_peers;
+int fftb200_peers_create(fftb200_peers** out, void* const* bases, int log_world, int rank);
+void fftb200_peers_destroy(fftb200_peers* peers);
+int fftb200_plan_set_peer_output(fftb200_plan* plan, const fftb200_peers* peers, int log_width, int log_rows_per_rank);
+/* First exchange: push `rows` rows of 2^(log_width + log_world) elements, split by destination column block, into the
+ * peers: rank g gets [rank * rows + t][c]. Enqueued on `stream` (a cudaStream_t). */
+int fftb200_push_columns(const fftb200_peers* peers, void* stream, const void* d_src, long long rows, int log_width);
+/* CUDA IPC handles (64 bytes) of buffers from fftb200_malloc, exchanged by the caller between the per-GPU processes */
+int fftb200_ipc_export(void* dptr, void* handle64);
+void* fftb200_ipc_open(const void* handle64);
+int fftb200_ipc_close(void* mapped);
 
 /* ---- timing on the plan's stream (CUDA events) ---- */
 int fftb200_timer_start(fftb200_plan* plan);

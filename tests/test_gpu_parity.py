@@ -273,15 +273,23 @@ def _dist_module():
 
 @pytest.mark.parametrize("log_n,direction", [(20, -1), (21, 1), (22, -1), (24, -1)])
 def test_distributed_plan_world_1_matches_the_oracle(gpu, port, O, log_n, direction):
-    """World size 1 runs the same head / tail partial plans and rank table as any rank of a multi-GPU job."""
+    """World size 1 runs the same head / tail partial plans, rank table, push kernel and peer-store epilogue (onto
+    itself) as any rank of a multi-GPU job; both drivers."""
     import torch
     D = _dist_module()
     n = 1 << log_n
-    plan = D.DistFFT(n, 1, 0, lambda *a: D.CudaBackend(gpu, *a), direction=direction)
     x = port.fill(45, 0, n)
+    want = port.fft(x, direction)
+    plan = D.DistFFT(n, 1, 0, lambda *a: D.CudaBackend(gpu, *a), direction=direction)
     y = plan.execute(torch.from_numpy(x).cuda())
     torch.cuda.synchronize()
-    assert O.rel_l2(y.cpu().numpy(), port.fft(x, direction)) <= TOL
+    assert O.rel_l2(y.cpu().numpy(), want) <= TOL
+    plan.close()
+    plan = D.DistFFTP2P(gpu, n, 1, 0, direction=direction)
+    for _ in range(2):
+        y = plan.execute(torch.from_numpy(x).cuda())
+        torch.cuda.synchronize()
+        assert O.rel_l2(y.cpu().numpy(), want) <= TOL
     plan.close()
 
 
@@ -293,10 +301,11 @@ def test_distributed_two_ranks_match_the_single_gpu_plan(gpu):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
-                        "--master-port", "29533", os.path.join(root, "tools", "dist_check.py"), "22", "24", "--inverse", "--notime"],
-                       capture_output=True, text=True, timeout=600)
-    assert r.returncode == 0, r.stderr[-2000:]
     import json
-    errs = [json.loads(l)["rel_l2_vs_single_gpu_plan"] for l in r.stdout.replace("}{", "}\n{").splitlines() if l.startswith("{")]
-    assert len(errs) == 8 and max(errs) <= TOL
+    for extra in ([], ["--nccl"]):   # fused P2P exchanges (the product) and the NCCL all-to-all baseline driver
+        r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                            "--master-port", "29533", os.path.join(root, "tools", "dist_check.py"), "22", "24", "--inverse", "--notime"] + extra,
+                           capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stderr[-2000:]
+        errs = [json.loads(l)["rel_l2_vs_single_gpu_plan"] for l in r.stdout.replace("}{", "}\n{").splitlines() if l.startswith("{")]
+        assert len(errs) == 8 and max(errs) <= TOL
