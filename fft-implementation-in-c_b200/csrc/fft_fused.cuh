@@ -64,6 +64,7 @@ struct FusedArgs {
     int lag;            // pass B of group g is scheduled after pass A of group g + lag
     int slots;          // scratch ring depth in groups (>= lag + 1)
     int inverse;        // selects the INV instantiation (conjugate in, conjugate + scale out)
+    int log_cb;         // column mode: log2 of the 16-column blocks per transform (row length / 16)
     int debug;          // development only: 1 = pass A alone, 2 = pass B alone, 4 = ignore the dependency counters
     double scale;       // 1/N for the inverse
     cd dtw[3][16];      // pass B, sub-pass j: dtw[j][h] = T[stage][q << a_tot] (table entry at kappa = 0), h = 2^(s-1) + q
@@ -163,6 +164,15 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* tm, in
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* tm, int x, int y, const void* src, uint64_t pol) {
     asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group.L2::cache_hint [%0, {%1, %2}], [%3], %4;"
                  ::"l"(tm), "r"(x), "r"(y), "r"(smem_u32(src)), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* tm, int c0, int c1, int c2, int c3, uint64_t* bar, uint64_t pol) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%2, %3, %4, %5}], [%6], %7;"
+        ::"r"(smem_u32(dst)), "l"(tm), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(smem_u32(bar)), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* tm, int c0, int c1, int c2, int c3, const void* src, uint64_t pol) {
+    asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.tile.bulk_group.L2::cache_hint [%0, {%1, %2, %3, %4}], [%5], %6;"
+                 ::"l"(tm), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(smem_u32(src)), "l"(pol) : "memory");
 }
 __device__ __forceinline__ void bulk_load_hint(void* dst, const void* src, uint32_t bytes, uint64_t* bar, uint64_t pol) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
@@ -267,12 +277,18 @@ __device__ __forceinline__ void fused_publish(int* counter) {
     atomicAdd(counter, 1);
 }
 
-template <int LM, int LR, bool INV>
+// COLS (column mode, LM = LR = 8): the 2^16-point transforms run along t of a row-major [t][c] array with rows of
+// 16 * 2^log_cb contiguous columns c - stages 1 .. 16 of a larger transform N = 2^16 * row length (head of a plan
+// that ends with one LAST tile pass). Tiles are 16 columns x 256 points in both passes, a "virtual transform" is one
+// 16-column block (2^20 points, 256 tiles per pass); the pass-B twiddles T[8 + s][k_hi + 256 q] are uniform per tile.
+template <int LM, int LR, bool INV, bool COLS = false>
 __global__ void __launch_bounds__(FUSED_THREADS, 1)
 fft_fused_kernel(const FusedArgs a, const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUtensorMap tm_sc,
                  const __grid_constant__ CUtensorMap tm_out) {
     static_assert(LM >= 6 && LM <= 10 && LR >= 6 && LR <= 10, "pass sizes 64 .. 1024");
-    constexpr int LOGN = LM + LR, LOG_TPT = LOGN - 12;
+    static_assert(!COLS || (LM == 8 && LR == 8), "column mode is built for 256 x 256");
+    constexpr int LOGN = COLS ? 20 : LM + LR;             // points per (virtual) transform
+    constexpr int LOG_TPT = LOGN - 12;
     constexpr int LC = 12 - LM, LC2 = 12 - LR;          // log2 columns per A tile / k's per B tile
     constexpr int A3 = LM >= 9, B3 = LR >= 9;            // three sub-passes?
     constexpr int RA0 = A3 ? LM - 8 : LM - 4, RB0 = B3 ? LR - 8 : LR - 4;
@@ -341,7 +357,10 @@ fft_fused_kernel(const FusedArgs a, const __grid_constant__ CUtensorMap tm_in, c
 #pragma unroll
                 for (int q = 0; q < 4; q++) {
                     waitq(q);
-                    tma_load_2d(buf + q * QT, &tm_in, 2 * (blk << LC), (int)((tr << LM) + q * (QT >> LC)), &full[w], pol_first);
+                    if constexpr (COLS)   // [b][t_hi][t_lo][c]: 16 columns of block cb, t_lo = blk, a quarter of the t_hi range
+                        tma_load_4d(buf + q * QT, &tm_in, 32 * (int)(tr & ((1 << a.log_cb) - 1)), blk, q * 64, (int)(tr >> a.log_cb), &full[w], pol_first);
+                    else
+                        tma_load_2d(buf + q * QT, &tm_in, 2 * (blk << LC), (int)((tr << LM) + q * (QT >> LC)), &full[w], pol_first);
                 }
             }
         };
@@ -394,14 +413,18 @@ fft_fused_kernel(const FusedArgs a, const __grid_constant__ CUtensorMap tm_in, c
                     const long long trl = (long long)(cur_it.g % a.slots) * a.gt + trg;
 #pragma unroll
                     for (int q = 0; q < 4; q++) {
-                        tma_store_2d(&tm_sc, 2 * (blk << LC), (int)((trl << LM) + q * (QT >> LC)), buf + q * QT, pol_last);
+                        if constexpr (COLS) tma_store_4d(&tm_sc, 0, blk, q * 64, (int)trl, buf + q * QT, pol_last);   // [slot][k_hi][t_lo][c16]
+                        else tma_store_2d(&tm_sc, 2 * (blk << LC), (int)((trl << LM) + q * (QT >> LC)), buf + q * QT, pol_last);
                         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                     }
                 } else {
                     const long long tr = (long long)cur_it.g * a.gt + trg;
 #pragma unroll
                     for (int q = 0; q < 4; q++) {
-                        tma_store_2d(&tm_out, 2 * (blk << LC2), (int)((tr << LR) + q * (QT >> LC2)), buf + q * QT, pol_first);
+                        if constexpr (COLS)   // [b][q][k_hi][c]
+                            tma_store_4d(&tm_out, 32 * (int)(tr & ((1 << a.log_cb) - 1)), blk, q * 64, (int)(tr >> a.log_cb), buf + q * QT, pol_first);
+                        else
+                            tma_store_2d(&tm_out, 2 * (blk << LC2), (int)((tr << LR) + q * (QT >> LC2)), buf + q * QT, pol_first);
                         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                     }
                 }
@@ -512,6 +535,39 @@ fft_fused_kernel(const FusedArgs a, const __grid_constant__ CUtensorMap tm_in, c
             // ------------------------------ pass B: stages LM + 1 .. LM + LR for C2 = 2^LC2 values of k ------------------------------
             // the scratch block is in shared memory now: its ring slot may be overwritten (a completed read needs no fence)
             if (t == 0 && !nowait) atomicAdd(a.flags + a.ngroups + kinds[4 * b + 2], 1);
+            if constexpr (COLS) {
+                // the tile is [t_lo][c16], the geometry of a pass-A tile; stages 9 .. 16 with T[8 + s][kb + 256 q]
+                typedef Geo<4, 8, 0, 0, 4, false> G0;
+                const G0 g0(t);
+                fused_gather<G0, SwzId, 4, false>(x, sm, g0);
+                {
+                    cd tw[16];
+                    fused_twiddles<4>(tw, a.tab + (kb - 1), 8, a.dtw[0]);
+                    SubStageGen<4, 1, 0, 0>::run(x, tw);
+                }
+                fused_scatter<G0, SwzId, 4>(x, sm, g0);   // in place per thread
+                group_sync(g2);
+                typedef Geo<4, 8, 0, 4, 4, false> G1;
+                const G1 g1(t);
+                fused_gather<G1, SwzId, 4, false>(x, sm, g1);
+                {
+                    cd tw[16];
+                    fused_twiddles<4>(tw, a.tab + (kb + (g1.kloc << 8) - 1), 12, a.dtw[2]);
+                    SubStageGen<4, 1, 0, 0>::run(x, tw);
+                }
+                group_sync(g2);   // every gather is done: stage [q][c16]
+                cd* p = sm + g1.lo + (g1.kloc << 4);
+#pragma unroll
+                for (int q = 0; q < 16; q++) {
+                    cd r = x[q];
+                    if (INV) r.y = -r.y;   // conjugate out; the scale belongs to the pass that ends the plan
+                    p[q << 8] = r;
+                }
+                fused_stage_done(&staged[b], t);
+                b += 2;
+                if (b >= PIPE_STAGES) { b -= PIPE_STAGES; n++; }
+                continue;
+            }
             typedef typename SwzBlast<LR>::type SWL;
             typedef typename std::conditional<B3, SwzId, SWL>::type SW1;   // layout after sub-pass 0
             {
@@ -595,6 +651,9 @@ inline const void* fused_func(int lm, int lr, int inverse) {
     if (!f) f = fused_func_3(lm, lr, inverse);
     return f;
 }
+// column mode (fft_kernels_fused1.cu)
+const void* fused_cols_func(int inverse);
+void launch_fused_cols(const FusedArgs& a, const CUtensorMap* tm, int grid, cudaStream_t s);
 // tm[0..2]: tensor maps of the input (pass-A loads), the scratch ring (pass-A stores) and the output (pass-B stores)
 inline bool launch_fused(int lm, int lr, const FusedArgs& a, const CUtensorMap* tm, int grid, cudaStream_t s) {
     return launch_fused_0(lm, lr, a, tm, grid, s) || launch_fused_1(lm, lr, a, tm, grid, s) ||

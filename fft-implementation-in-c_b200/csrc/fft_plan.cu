@@ -178,6 +178,7 @@ enum { ACC_N = 8192 };  // accurate tables cover stages m <= 8192 (SURVEY.md 7.0
 struct Pass {
     const KernelInfo* k;   // nullptr: persistent TMA kernel fft_pipe_kernel<log_p>, or the fused kernel when fused_lm > 0
     int fused_lm = 0, fused_lr = 0;   // fft_fused_kernel<fused_lm, fused_lr>: both passes in one launch
+    int fused_cols = 0;               // column mode: stages 1 .. 16 of a larger transform, rows of 2^(log_n - 16) columns
     int log_p;
     int log_m;
     int nt;        // whole-transform kernels: transforms per tile (tiles = ceil(nbatch / nt)); else 0
@@ -297,6 +298,33 @@ static int build_passes(fftb200_plan* p, DeviceState* ds) {
             return 0;
         }
     }
+    if (L >= 22 && L <= 25 && p->acc && !getenv("FFTB200_NO_FUSED") && !getenv("FFTB200_NO_FUSED_COLS") && !getenv("FFTB200_SPLIT")) {
+        // stages 1 .. 16 in the fused kernel's column mode (intermediate in L2), then one LAST tile pass: two HBM round trips
+        Pass fz;
+        fz.k = nullptr; fz.fused_lm = 8; fz.fused_lr = 8; fz.fused_cols = 1;
+        fz.log_p = 16; fz.log_m = 0; fz.nt = 0; fz.shift = 0;
+        fz.src = BUF_IN; fz.dst = BUF_SCRATCH; fz.final_pass = 0;
+        for (int iv = 0; iv < 2; iv++)
+            CU(cudaFuncSetAttribute(fused_cols_func(iv), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FUSED_SMEM));
+        fz.grid_max = ds->sms;
+        Pass lz;
+        lz.log_p = L - 16; lz.log_m = 16;
+        lz.k = find_kernel(MODE_LAST, lz.log_p, 0);
+        if (!lz.k) return fail("no last-pass kernel for 2^%d points", lz.log_p);
+        lz.nt = 0; lz.shift = 16 - lz.k->logc;
+        lz.src = BUF_SCRATCH; lz.dst = BUF_OUT; lz.final_pass = 1;
+        CU(cudaFuncSetAttribute(lz.k->func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lz.k->smem));
+        int occ = 0;
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, lz.k->func, lz.k->threads, lz.k->smem));
+        if (occ < 1) return fail("kernel variant does not fit on an SM");
+        lz.grid_max = persistent ? ds->sms * occ : 0x7fffffff;
+        p->passes.push_back(fz);
+        p->passes.push_back(lz);
+        char b[96];
+        snprintf(b, sizeof(b), "Zc8+8(fused, column mode)+L%d(occ%d)", lz.log_p, occ);
+        p->desc += b;
+        return 0;
+    }
     for (int i = 0; i < np; i++) {
         Pass ps;
         const int lp = sizes[i];
@@ -356,8 +384,11 @@ static EncodeTiledFn encode_tiled_fn() {
 }
 
 // Enqueue the fused two-pass kernel (fft_fused.cuh) for `nbatch` transforms.
-static int enqueue_fused(fftb200_plan* p, const Pass& ps, const cd* in, cd* out, int inverse, long long nbatch) {
-    const int L = p->log_n, lm = ps.fused_lm, lr = ps.fused_lr;
+static int enqueue_fused(fftb200_plan* p, const Pass& ps, const cd* in, cd* out, int inverse, long long nbatch_in) {
+    // column mode: a "transform" of the schedule is one 16-column block (2^20 points) of stages 1 .. 16
+    const int cols = ps.fused_cols, log_rw = p->log_n - 16, log_cb = cols ? log_rw - 4 : 0;
+    const int L = cols ? 20 : p->log_n, lm = ps.fused_lm, lr = ps.fused_lr;
+    const long long nbatch = cols ? nbatch_in << log_cb : nbatch_in;
     const long long tpt = 1LL << (L - 12);                  // 64 KB tiles per transform and pass
     long long gt = tpt >= 32 ? 1 : 32 / tpt;                // transforms per group: >= 32 tiles (2 MB)
     if (const char* e = getenv("FFTB200_FUSED_GT")) gt = atol(e);
@@ -367,8 +398,11 @@ static int enqueue_fused(fftb200_plan* p, const Pass& ps, const cd* in, cd* out,
     long long lag = (3 * ps.grid_max + T - 1) / T;           // ~3 tiles per CTA between the end of A(g) and B(g)
     if (const char* e = getenv("FFTB200_FUSED_LAG")) lag = atol(e);
     if (lag < 1) lag = 1;
+    // scratch ring: lag + 3 groups, but not more than 32 MB (what stays resident in L2 next to the streaming traffic;
+    // measured: 2^20 with 2 slots of 16 MB 2.90 ms, 3 slots 3.11 ms, 4 slots 3.27 ms)
     long long slots = lag + 3;
-    while (slots > lag + 1 && slots * T * PIPE_TILE * (long long)sizeof(cd) > (48LL << 20)) slots--;
+    while (slots > 2 && slots * T * PIPE_TILE * (long long)sizeof(cd) > (32LL << 20)) slots--;
+    if (lag > slots - 1 && !getenv("FFTB200_FUSED_LAG")) lag = slots - 1;
     if (const char* e = getenv("FFTB200_FUSED_SLOTS")) slots = atol(e);
     if (slots < lag + 1) slots = lag + 1;
     const long long G = (nbatch + gt - 1) / gt;
@@ -397,7 +431,7 @@ static int enqueue_fused(fftb200_plan* p, const Pass& ps, const cd* in, cd* out,
     if (const char* e = getenv("FFTB200_FUSED_PROMO")) promo = atoi(e);
     const CUtensorMapL2promotion pr = promo >= 2 ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B : promo == 1 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B
                                                                                                    : CU_TENSOR_MAP_L2_PROMOTION_NONE;
-    for (int i = 0; i < 3; i++) {
+    for (int i = 0; i < 3 && !cols; i++) {
         const int lcols = i == 2 ? lm : lr, lrows = i == 2 ? lr : lm;          // row length / rows per transform (log2)
         const long long ntr = i == 1 ? slots * gt : nbatch;
         void* base = i == 0 ? (void*)in : i == 1 ? (void*)p->fscratch : (void*)out;
@@ -409,10 +443,23 @@ static int enqueue_fused(fftb200_plan* p, const Pass& ps, const cd* in, cd* out,
                                CU_TENSOR_MAP_SWIZZLE_NONE, i == 0 ? pr : CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled failed (%d) for map %d", (int)r, i);
     }
+    for (int i = 0; i < 3 && cols; i++) {
+        // input / output: [b][t_hi or q][t_lo or k_hi][c] with rows of 2^log_rw columns; scratch ring: [slot][k_hi][t_lo][c16]
+        const bool sc = i == 1;
+        void* base = i == 0 ? (void*)in : sc ? (void*)p->fscratch : (void*)out;
+        const cuuint64_t rowb = sc ? 16 * sizeof(cd) : (cuuint64_t)sizeof(cd) << log_rw;
+        const cuuint64_t gdim[4] = {sc ? 32u : (cuuint64_t)2 << log_rw, 256, 256, (cuuint64_t)(sc ? slots * gt : nbatch_in)};
+        const cuuint64_t gstr[3] = {rowb, 256 * rowb, 65536 * rowb};
+        const cuuint32_t box[4] = {32, 1, 64, 1};
+        const cuuint32_t estr[4] = {1, 1, 1, 1};
+        const CUresult r = enc(&tm[i], CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 4, base, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled failed (%d) for column-mode map %d", (int)r, i);
+    }
     FusedArgs fa;
     fa.scratch = p->fscratch; fa.tab = p->tab; fa.acc = p->acc; fa.flags = p->fflags;
     fa.nbatch = nbatch; fa.gt = (int)gt; fa.ngroups = (int)G; fa.lag = (int)lag; fa.slots = (int)slots;
-    fa.inverse = inverse; fa.scale = p->scale;
+    fa.inverse = inverse; fa.scale = cols ? 1.0 : p->scale; fa.log_cb = log_cb;
     fa.debug = getenv("FFTB200_FUSED_DEBUG") ? atoi(getenv("FFTB200_FUSED_DEBUG")) : 0;
     memcpy(fa.dtw, p->fdtw, sizeof(fa.dtw));
     fa.prof = nullptr;
@@ -423,7 +470,8 @@ static int enqueue_fused(fftb200_plan* p, const Pass& ps, const cd* in, cd* out,
 #endif
     const long long items = 2 * nbatch * tpt;
     const int grid = (int)(items < ps.grid_max ? items : ps.grid_max);
-    if (!launch_fused(lm, lr, fa, tm, grid, p->stream)) return fail("no fused kernel for 2^%d x 2^%d", lm, lr);
+    if (cols) launch_fused_cols(fa, tm, grid, p->stream);
+    else if (!launch_fused(lm, lr, fa, tm, grid, p->stream)) return fail("no fused kernel for 2^%d x 2^%d", lm, lr);
     CU(cudaGetLastError());
 #ifdef FUSED_PROF
     if (getenv("FFTB200_FUSED_PROF_PRINT")) {
@@ -459,33 +507,16 @@ static int ensure_scratch(fftb200_plan* p, long long nbatch) {
 }
 
 // Enqueue the power-of-two c2c passes: `inverse` selects conjugated twiddles and the 1/m scale.
-static int enqueue_c2c_range(fftb200_plan* p, const cd* in, cd* out, int inverse, long long nbatch);
-
 static int enqueue_c2c(fftb200_plan* p, const cd* in, cd* out, int inverse, long long nbatch) {
-    if (nbatch <= 0) return 0;
-    // EXPERIMENT: run multi-pass plans group by group so the intermediate stays in L2
-    if (p->passes.size() >= 2 && getenv("FFTB200_GROUP_MB")) {
-        long long gb = ((long long)atol(getenv("FFTB200_GROUP_MB")) << 20) / ((long long)sizeof(cd) << p->log_n);
-        if (gb < 1) gb = 1;
-        if (gb < nbatch) {
-            for (long long b0 = 0; b0 < nbatch; b0 += gb) {
-                const long long nb = nbatch - b0 < gb ? nbatch - b0 : gb;
-                if (enqueue_c2c_range(p, in + (b0 << p->log_n), out + (b0 << p->log_n), inverse, nb) != 0) return -1;
-            }
-            return 0;
-        }
-    }
-    return enqueue_c2c_range(p, in, out, inverse, nbatch);
-}
-
-static int enqueue_c2c_range(fftb200_plan* p, const cd* in, cd* out, int inverse, long long nbatch) {
     if (nbatch <= 0) return 0;
     if (ensure_scratch(p, nbatch) != 0) return -1;
     for (const Pass& ps : p->passes) {
         const long long ntiles = pass_tiles(ps, nbatch);
         const int grid = (int)(ntiles < ps.grid_max ? ntiles : ps.grid_max);
         if (ps.fused_lm) {
-            if (enqueue_fused(p, ps, in, out, inverse, nbatch) != 0) return -1;
+            const cd* fsrc = ps.src == BUF_IN ? in : ps.src == BUF_OUT ? out : p->scratch;
+            cd* fdst = ps.dst == BUF_OUT ? out : p->scratch;
+            if (enqueue_fused(p, ps, fsrc, fdst, inverse, nbatch) != 0) return -1;
             continue;
         }
         if (!ps.k) {
@@ -581,7 +612,7 @@ extern "C" int fftb200_plan_create(fftb200_plan** out, const fftb200_plan_desc* 
         p->desc = head;
         if ((rc = build_passes(p, ds)) != 0) break;
         p->launches = (int)p->passes.size();
-        if (p->passes.size() == 1 && p->passes[0].fused_lm) {
+        if (!p->passes.empty() && p->passes[0].fused_lm) {
             // dtw[j][h] = table entry (h << a_tot_j) - 1: stage a_tot_j + s, index q << a_tot_j, h = 2^(s-1) + q
             if (!d->twiddles || d->table_n < p->m) { rc = fail("fused plan needs the host twiddle table"); break; }
             const int lm = p->passes[0].fused_lm, lr = p->passes[0].fused_lr;
