@@ -45,6 +45,7 @@
 // tools/l2bench.cu: TMA stores 26 B/clk/SM, loads 69 B/clk/SM) idles about half of the time.
 #pragma once
 #include <cuda.h>
+#include <string.h>
 
 #include <type_traits>
 
@@ -638,12 +639,11 @@ fft_fused_kernel(const FusedArgs a, const __grid_constant__ CUtensorMap tm_in, c
 #endif
 }
 
-// defined in fft_kernels_fused{0..3}.cu: nullptr / false when the (lm, lr) pair is not compiled in that unit
-#define FUSED_UNIT_DECL(I)                                                    \
-    const void* fused_func_##I(int lm, int lr, int inverse);                  \
-    bool launch_fused_##I(int lm, int lr, const FusedArgs& a, const CUtensorMap* tm, int grid, cudaStream_t s);
-FUSED_UNIT_DECL(0) FUSED_UNIT_DECL(1) FUSED_UNIT_DECL(2) FUSED_UNIT_DECL(3)
-#undef FUSED_UNIT_DECL
+// defined in fft_kernels_fused{0..3}.cu: nullptr when the (lm, lr) pair is not compiled in that unit
+const void* fused_func_0(int lm, int lr, int inverse);
+const void* fused_func_1(int lm, int lr, int inverse);
+const void* fused_func_2(int lm, int lr, int inverse);
+const void* fused_func_3(int lm, int lr, int inverse);
 inline const void* fused_func(int lm, int lr, int inverse) {
     const void* f = fused_func_0(lm, lr, inverse);
     if (!f) f = fused_func_1(lm, lr, inverse);
@@ -651,13 +651,20 @@ inline const void* fused_func(int lm, int lr, int inverse) {
     if (!f) f = fused_func_3(lm, lr, inverse);
     return f;
 }
-// column mode (fft_kernels_fused1.cu)
-const void* fused_cols_func(int inverse);
-void launch_fused_cols(const FusedArgs& a, const CUtensorMap* tm, int grid, cudaStream_t s);
-// tm[0..2]: tensor maps of the input (pass-A loads), the scratch ring (pass-A stores) and the output (pass-B stores)
-inline bool launch_fused(int lm, int lr, const FusedArgs& a, const CUtensorMap* tm, int grid, cudaStream_t s) {
-    return launch_fused_0(lm, lr, a, tm, grid, s) || launch_fused_1(lm, lr, a, tm, grid, s) ||
-           launch_fused_2(lm, lr, a, tm, grid, s) || launch_fused_3(lm, lr, a, tm, grid, s);
+const void* fused_cols_func(int inverse);   // column mode (fft_kernels_fused1.cu)
+
+// tm[0..2]: tensor maps of the input (pass-A loads), the scratch ring (pass-A stores) and the output (pass-B stores).
+// The CTAs synchronise through global counters, so all of them must be resident: a cooperative launch makes the
+// driver guarantee that (or fail) even when other kernels compete for the SMs.
+inline cudaError_t launch_fused(const void* func, const FusedArgs& a, const CUtensorMap* tm, int grid, cudaStream_t s) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(FUSED_THREADS); cfg.dynamicSmemBytes = FUSED_SMEM; cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeCooperative; at[0].val.cooperative = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    void* args[4] = {(void*)&a, (void*)&tm[0], (void*)&tm[1], (void*)&tm[2]};
+    return cudaLaunchKernelExC(&cfg, func, args);
 }
 
 }  // namespace fftb200

@@ -398,10 +398,10 @@ static int enqueue_fused(fftb200_plan* p, const Pass& ps, const cd* in, cd* out,
     long long lag = (3 * ps.grid_max + T - 1) / T;           // ~3 tiles per CTA between the end of A(g) and B(g)
     if (const char* e = getenv("FFTB200_FUSED_LAG")) lag = atol(e);
     if (lag < 1) lag = 1;
-    // scratch ring: lag + 3 groups, but not more than 32 MB (what stays resident in L2 next to the streaming traffic;
+    // scratch ring: lag + 3 groups, but not more than 36 MB (about what stays resident in L2 next to the streaming traffic;
     // measured: 2^20 with 2 slots of 16 MB 2.90 ms, 3 slots 3.11 ms, 4 slots 3.27 ms)
     long long slots = lag + 3;
-    while (slots > 2 && slots * T * PIPE_TILE * (long long)sizeof(cd) > (32LL << 20)) slots--;
+    while (slots > 2 && slots * T * PIPE_TILE * (long long)sizeof(cd) > (36LL << 20)) slots--;
     if (lag > slots - 1 && !getenv("FFTB200_FUSED_LAG")) lag = slots - 1;
     if (const char* e = getenv("FFTB200_FUSED_SLOTS")) slots = atol(e);
     if (slots < lag + 1) slots = lag + 1;
@@ -470,9 +470,9 @@ static int enqueue_fused(fftb200_plan* p, const Pass& ps, const cd* in, cd* out,
 #endif
     const long long items = 2 * nbatch * tpt;
     const int grid = (int)(items < ps.grid_max ? items : ps.grid_max);
-    if (cols) launch_fused_cols(fa, tm, grid, p->stream);
-    else if (!launch_fused(lm, lr, fa, tm, grid, p->stream)) return fail("no fused kernel for 2^%d x 2^%d", lm, lr);
-    CU(cudaGetLastError());
+    const void* func = cols ? fused_cols_func(inverse) : fused_func(lm, lr, inverse);
+    if (!func) return fail("no fused kernel for 2^%d x 2^%d", lm, lr);
+    CU(launch_fused(func, fa, tm, grid, p->stream));
 #ifdef FUSED_PROF
     if (getenv("FFTB200_FUSED_PROF_PRINT")) {
         CU(cudaStreamSynchronize(p->stream));

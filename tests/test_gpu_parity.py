@@ -243,6 +243,31 @@ def test_fused_two_pass_many_groups(gpu, port, O, log_n, batch):
     L.fft_gpu_destroy_plan(inv)
 
 
+def test_two_fused_plans_run_concurrently(gpu, port, O):
+    """The fused kernel's CTAs synchronise through global counters and must all be resident; it is launched
+    cooperatively, so two plans enqueued back to back on their own streams must both finish with the right answer."""
+    import torch
+    L = gpu.lib
+    n, batch = 1 << 16, 300
+    x = torch.empty((2, batch, n), dtype=torch.complex128, device="cuda")
+    y = torch.empty_like(x)
+    assert L.fftb200_fill_splitmix(x.data_ptr(), 49, 0, 2 * n * batch) == 0
+    torch.cuda.synchronize()
+    plans = [L.fft_gpu_plan_1d(n, batch, -1) for _ in range(2)]
+    for rep in range(3):
+        for i, pl in enumerate(plans):
+            assert L.fftb200_plan_exec_async(L.fftb200_engine_of(pl), x[i].data_ptr(), y[i].data_ptr()) == 0
+    for pl in plans:
+        assert L.fftb200_plan_sync(L.fftb200_engine_of(pl)) == 0
+    for i in range(2):
+        rows = [0, 17, batch - 1]
+        got = y[i][rows].cpu().numpy()
+        xin = np.stack([port.fill(49, (i * batch + r) * n, n) for r in rows])
+        assert O.rel_l2(got, port.fft_batch(xin, -1)) <= TOL
+    for pl in plans:
+        L.fft_gpu_destroy_plan(pl)
+
+
 def test_config3_linearity_at_2_24(gpu):
     import torch
     L = gpu.lib
