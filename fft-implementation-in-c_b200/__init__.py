@@ -105,6 +105,7 @@ _SIGS = {
     "fftb200_engine_of": (_vp, [_vp]),
     "fftb200_devptr_of": (_vp, [_vp]),
     "fftb200_host_twiddles": (_vp, [C.c_int]),
+    "fftb200_host_twiddles_accurate": (_vp, [C.POINTER(C.c_int)]),
     "fftb200_host_chirp": (None, [_vp, C.c_int, C.c_int]),
     "fftb200_host_tables_release": (None, []),
     "fftb200_host_twiddles_dist": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_int]),
@@ -171,6 +172,35 @@ def r2c(x):
     lib.fft_execute(plan)
     lib.fft_destroy_plan(plan)
     return out
+
+
+class PlanDesc(C.Structure):
+    """struct fftb200_plan_desc (include/fftb200.h)"""
+    _fields_ = [("n", C.c_int), ("batch", C.c_int), ("direction", C.c_int), ("kind", C.c_int),
+                ("twiddles", C.c_void_p), ("table_n", C.c_int), ("chirp", C.c_void_p),
+                ("twiddles_accurate", C.c_void_p), ("accurate_n", C.c_int), ("flags", C.c_uint)]
+
+
+def engine_plan(n, batch, kind=FFTB200_C2C, direction=FFT_FORWARD):
+    """fftb200_plan_create with the host tables the C99 host library would pass (host/fft_gpu.c): returns the plan handle.
+    R2C / BLUESTEIN have no batched entry point in the reference's public API; the engine plan is the batched form."""
+    m = n
+    keep = None
+    d = PlanDesc(n, batch, direction, kind, None, 0, None, None, 0, 0)
+    if kind == FFTB200_BLUESTEIN:
+        m = 1
+        while m < 2 * n - 1:
+            m <<= 1
+        keep = host_chirp(n, direction)
+        d.chirp = keep.ctypes.data
+    d.twiddles, d.table_n = lib.fftb200_host_twiddles(m), m
+    an = C.c_int()
+    d.twiddles_accurate = lib.fftb200_host_twiddles_accurate(C.byref(an))
+    d.accurate_n = an.value
+    plan = _vp()
+    if lib.fftb200_plan_create(C.byref(plan), C.byref(d)) != 0:
+        raise RuntimeError("fftb200_plan_create failed: " + lib.fftb200_last_error().decode())
+    return plan
 
 
 def host_twiddles(n):

@@ -65,6 +65,7 @@ struct FusedArgs {
     int lag;            // pass B of group g is scheduled after pass A of group g + lag
     int slots;          // scratch ring depth in groups (>= lag + 1)
     int inverse;        // selects the INV instantiation (conjugate in, conjugate + scale out)
+    cd* out;            // r2c mode: output base (the Nyquist bin of every transform is stored by a plain bulk copy)
     int log_cb;         // column mode: log2 of the 16-column blocks per transform (row length / 16)
     int debug;          // development only: 1 = pass A alone, 2 = pass B alone, 4 = ignore the dependency counters
     double scale;       // 1/N for the inverse
@@ -175,6 +176,13 @@ __device__ __forceinline__ void tma_store_4d(const CUtensorMap* tm, int c0, int 
     asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.tile.bulk_group.L2::cache_hint [%0, {%1, %2, %3, %4}], [%5], %6;"
                  ::"l"(tm), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(smem_u32(src)), "l"(pol) : "memory");
 }
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* tm, int c0, int c1, int c2, const void* src, uint64_t pol) {
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.tile.bulk_group.L2::cache_hint [%0, {%1, %2, %3}], [%4], %5;"
+                 ::"l"(tm), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(src)), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void bulk_store(void* dst, const void* src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(src)), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ void bulk_load_hint(void* dst, const void* src, uint32_t bytes, uint64_t* bar, uint64_t pol) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
                  ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(pol) : "memory");
@@ -218,6 +226,14 @@ struct FusedCursor {
 };
 
 // ---- sub-pass building blocks ---------------------------------------------------------------------------------
+// the tile holds 4096 REAL values (first half of the buffer): promote to complex while gathering (fft_auto.c:394-397)
+template <class G, int R>
+__device__ __forceinline__ void fused_gather_real(cd* x, const cd* sm, const G& g) {
+    const double* sr = reinterpret_cast<const double*>(sm);
+    const int base = g.gbase();
+#pragma unroll
+    for (int rho = 0; rho < (1 << R); rho++) x[bitrev_c<R>(rho)] = make_double2(sr[base + rho * G::GSTRIDE], 0.0);
+}
 template <class G, class SW, int R, bool CONJ>
 __device__ __forceinline__ void fused_gather(cd* x, const cd* sm, const G& g) {
     const int base = g.gbase();
@@ -282,12 +298,16 @@ __device__ __forceinline__ void fused_publish(int* counter) {
 // 16 * 2^log_cb contiguous columns c - stages 1 .. 16 of a larger transform N = 2^16 * row length (head of a plan
 // that ends with one LAST tile pass). Tiles are 16 columns x 256 points in both passes, a "virtual transform" is one
 // 16-column block (2^20 points, 256 tiles per pass); the pass-B twiddles T[8 + s][k_hi + 256 q] are uniform per tile.
-template <int LM, int LR, bool INV, bool COLS = false>
+// R2C (forward only): the input is real (n doubles per transform, promoted in the first gather) and only the bins
+// 0 .. n/2 are stored (n/2 + 1 per transform, fft_auto.h:89-97) - the reference's promote-then-c2c reading of
+// fft_plan_r2c_1d without the separate promotion and extraction passes.
+template <int LM, int LR, bool INV, bool COLS = false, bool R2C = false>
 __global__ void __launch_bounds__(FUSED_THREADS, 1)
 fft_fused_kernel(const FusedArgs a, const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUtensorMap tm_sc,
                  const __grid_constant__ CUtensorMap tm_out) {
     static_assert(LM >= 6 && LM <= 10 && LR >= 6 && LR <= 10, "pass sizes 64 .. 1024");
     static_assert(!COLS || (LM == 8 && LR == 8), "column mode is built for 256 x 256");
+    static_assert(!R2C || (!INV && !COLS), "r2c is a forward transform of whole arrays");
     constexpr int LOGN = COLS ? 20 : LM + LR;             // points per (virtual) transform
     constexpr int LOG_TPT = LOGN - 12;
     constexpr int LC = 12 - LM, LC2 = 12 - LR;          // log2 columns per A tile / k's per B tile
@@ -344,7 +364,7 @@ fft_fused_kernel(const FusedArgs a, const __grid_constant__ CUtensorMap tm_in, c
             const int blk = (int)(x.tau & ((1 << LOG_TPT) - 1));
             const long long trg = x.tau >> LOG_TPT;
             kinds[4 * w] = x.is_b; kinds[4 * w + 1] = blk; kinds[4 * w + 2] = x.g;
-            mbar_expect_tx(&full[w], PIPE_TILE * (uint32_t)sizeof(cd));
+            mbar_expect_tx(&full[w], (R2C && !x.is_b) ? PIPE_TILE * (uint32_t)sizeof(double) : PIPE_TILE * (uint32_t)sizeof(cd));
             if (x.is_b) {
                 asm volatile("fence.proxy.async;" ::: "memory");
                 const cd* src = a.scratch + (((size_t)(x.g % a.slots) * a.gt) << LOGN) + (size_t)x.tau * PIPE_TILE;
@@ -358,7 +378,9 @@ fft_fused_kernel(const FusedArgs a, const __grid_constant__ CUtensorMap tm_in, c
 #pragma unroll
                 for (int q = 0; q < 4; q++) {
                     waitq(q);
-                    if constexpr (COLS)   // [b][t_hi][t_lo][c]: 16 columns of block cb, t_lo = blk, a quarter of the t_hi range
+                    if constexpr (R2C)    // real rows: a quarter is 1024 doubles
+                        tma_load_2d(reinterpret_cast<double*>(buf) + q * QT, &tm_in, blk << LC, (int)((tr << LM) + q * (QT >> LC)), &full[w], pol_first);
+                    else if constexpr (COLS)   // [b][t_hi][t_lo][c]: 16 columns of block cb, t_lo = blk, a quarter of the t_hi range
                         tma_load_4d(buf + q * QT, &tm_in, 32 * (int)(tr & ((1 << a.log_cb) - 1)), blk, q * 64, (int)(tr >> a.log_cb), &full[w], pol_first);
                     else
                         tma_load_2d(buf + q * QT, &tm_in, 2 * (blk << LC), (int)((tr << LM) + q * (QT >> LC)), &full[w], pol_first);
@@ -422,7 +444,10 @@ fft_fused_kernel(const FusedArgs a, const __grid_constant__ CUtensorMap tm_in, c
                     const long long tr = (long long)cur_it.g * a.gt + trg;
 #pragma unroll
                     for (int q = 0; q < 4; q++) {
-                        if constexpr (COLS)   // [b][q][k_hi][c]
+                        if constexpr (R2C) {   // rows q < R/2 (bins below n/2) are the first two quarters; then the Nyquist bin X[M R/2]
+                            if (q < 2) tma_store_3d(&tm_out, 2 * (blk << LC2), q * (QT >> LC2), (int)tr, buf + q * QT, pol_first);
+                            else if (q == 2 && blk == 0) bulk_store(a.out + (size_t)tr * ((1 << (LOGN - 1)) + 1) + (1 << (LOGN - 1)), buf + 2 * QT, sizeof(cd));
+                        } else if constexpr (COLS)   // [b][q][k_hi][c]
                             tma_store_4d(&tm_out, 32 * (int)(tr & ((1 << a.log_cb) - 1)), blk, q * 64, (int)(tr >> a.log_cb), buf + q * QT, pol_first);
                         else
                             tma_store_2d(&tm_out, 2 * (blk << LC2), (int)((tr << LR) + q * (QT >> LC2)), buf + q * QT, pol_first);
@@ -493,12 +518,24 @@ fft_fused_kernel(const FusedArgs a, const __grid_constant__ CUtensorMap tm_in, c
             {
                 typedef Geo<LC, LM, 0, 0, RA0, false> G0;
                 constexpr int NB = 16 >> RA0, R0 = 1 << RA0;
+                if constexpr (R2C) {
+                    // the complex results overwrite other threads' real inputs: gather everything first
 #pragma unroll
-                for (int bb = 0; bb < NB; bb++) {
-                    const G0 g(t + PIPE_GROUP * bb);
-                    fused_gather<G0, SwzId, RA0, INV>(&x[bb * R0], sm, g);
-                    SubStageExact<RA0, 1, 0, 0>::run(&x[bb * R0]);
-                    fused_scatter<G0, SwzId, RA0>(&x[bb * R0], sm, g);
+                    for (int bb = 0; bb < NB; bb++) fused_gather_real<G0, RA0>(&x[bb * R0], sm, G0(t + PIPE_GROUP * bb));
+                    group_sync(g2);
+#pragma unroll
+                    for (int bb = 0; bb < NB; bb++) {
+                        SubStageExact<RA0, 1, 0, 0>::run(&x[bb * R0]);
+                        fused_scatter<G0, SwzId, RA0>(&x[bb * R0], sm, G0(t + PIPE_GROUP * bb));
+                    }
+                } else {
+#pragma unroll
+                    for (int bb = 0; bb < NB; bb++) {
+                        const G0 g(t + PIPE_GROUP * bb);
+                        fused_gather<G0, SwzId, RA0, INV>(&x[bb * R0], sm, g);
+                        SubStageExact<RA0, 1, 0, 0>::run(&x[bb * R0]);
+                        fused_scatter<G0, SwzId, RA0>(&x[bb * R0], sm, g);
+                    }
                 }
             }
             group_sync(g2);
@@ -652,6 +689,17 @@ inline const void* fused_func(int lm, int lr, int inverse) {
     return f;
 }
 const void* fused_cols_func(int inverse);   // column mode (fft_kernels_fused1.cu)
+const void* fused_r2c_func_0(int lm, int lr);
+const void* fused_r2c_func_1(int lm, int lr);
+const void* fused_r2c_func_2(int lm, int lr);
+const void* fused_r2c_func_3(int lm, int lr);
+inline const void* fused_r2c_func(int lm, int lr) {
+    const void* f = fused_r2c_func_0(lm, lr);
+    if (!f) f = fused_r2c_func_1(lm, lr);
+    if (!f) f = fused_r2c_func_2(lm, lr);
+    if (!f) f = fused_r2c_func_3(lm, lr);
+    return f;
+}
 
 // tm[0..2]: tensor maps of the input (pass-A loads), the scratch ring (pass-A stores) and the output (pass-B stores).
 // The CTAs synchronise through global counters, so all of them must be resident: a cooperative launch makes the

@@ -384,7 +384,7 @@ static EncodeTiledFn encode_tiled_fn() {
 }
 
 // Enqueue the fused two-pass kernel (fft_fused.cuh) for `nbatch` transforms.
-static int enqueue_fused(fftb200_plan* p, const Pass& ps, const cd* in, cd* out, int inverse, long long nbatch_in) {
+static int enqueue_fused(fftb200_plan* p, const Pass& ps, const cd* in, cd* out, int inverse, long long nbatch_in, int r2c = 0) {
     // column mode: a "transform" of the schedule is one 16-column block (2^20 points) of stages 1 .. 16
     const int cols = ps.fused_cols, log_rw = p->log_n - 16, log_cb = cols ? log_rw - 4 : 0;
     const int L = cols ? 20 : p->log_n, lm = ps.fused_lm, lr = ps.fused_lr;
@@ -431,7 +431,24 @@ static int enqueue_fused(fftb200_plan* p, const Pass& ps, const cd* in, cd* out,
     if (const char* e = getenv("FFTB200_FUSED_PROMO")) promo = atoi(e);
     const CUtensorMapL2promotion pr = promo >= 2 ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B : promo == 1 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B
                                                                                                    : CU_TENSOR_MAP_L2_PROMOTION_NONE;
+    if (r2c) {
+        // real input rows of R doubles; output bins 0 .. n/2 - 1 as [b][q < R/2][k] with n/2 + 1 elements per transform
+        const cuuint64_t gdim[2] = {(cuuint64_t)1 << lr, (cuuint64_t)nbatch << lm};
+        const cuuint64_t gstr[1] = {(cuuint64_t)sizeof(double) << lr};
+        const cuuint32_t box[2] = {(cuuint32_t)1 << (12 - lm), (cuuint32_t)1 << (lm - 2)};
+        const cuuint32_t estr[3] = {1, 1, 1};
+        CUresult r = enc(&tm[0], CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, (void*)in, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled failed (%d) for the real input", (int)r);
+        const cuuint64_t odim[3] = {(cuuint64_t)2 << lm, (cuuint64_t)1 << (lr - 1), (cuuint64_t)nbatch};
+        const cuuint64_t ostr[2] = {(cuuint64_t)sizeof(cd) << lm, (cuuint64_t)sizeof(cd) * (((cuuint64_t)1 << (L - 1)) + 1)};
+        const cuuint32_t obox[3] = {(cuuint32_t)2 << (12 - lr), (cuuint32_t)1 << (lr - 2), 1};
+        r = enc(&tm[2], CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, (void*)out, odim, ostr, obox, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled failed (%d) for the half spectrum", (int)r);
+    }
     for (int i = 0; i < 3 && !cols; i++) {
+        if (r2c && i != 1) continue;
         const int lcols = i == 2 ? lm : lr, lrows = i == 2 ? lr : lm;          // row length / rows per transform (log2)
         const long long ntr = i == 1 ? slots * gt : nbatch;
         void* base = i == 0 ? (void*)in : i == 1 ? (void*)p->fscratch : (void*)out;
@@ -459,7 +476,7 @@ static int enqueue_fused(fftb200_plan* p, const Pass& ps, const cd* in, cd* out,
     FusedArgs fa;
     fa.scratch = p->fscratch; fa.tab = p->tab; fa.acc = p->acc; fa.flags = p->fflags;
     fa.nbatch = nbatch; fa.gt = (int)gt; fa.ngroups = (int)G; fa.lag = (int)lag; fa.slots = (int)slots;
-    fa.inverse = inverse; fa.scale = cols ? 1.0 : p->scale; fa.log_cb = log_cb;
+    fa.inverse = inverse; fa.scale = cols ? 1.0 : p->scale; fa.log_cb = log_cb; fa.out = out;
     fa.debug = getenv("FFTB200_FUSED_DEBUG") ? atoi(getenv("FFTB200_FUSED_DEBUG")) : 0;
     memcpy(fa.dtw, p->fdtw, sizeof(fa.dtw));
     fa.prof = nullptr;
@@ -470,7 +487,7 @@ static int enqueue_fused(fftb200_plan* p, const Pass& ps, const cd* in, cd* out,
 #endif
     const long long items = 2 * nbatch * tpt;
     const int grid = (int)(items < ps.grid_max ? items : ps.grid_max);
-    const void* func = cols ? fused_cols_func(inverse) : fused_func(lm, lr, inverse);
+    const void* func = r2c ? fused_r2c_func(lm, lr) : cols ? fused_cols_func(inverse) : fused_func(lm, lr, inverse);
     if (!func) return fail("no fused kernel for 2^%d x 2^%d", lm, lr);
     CU(launch_fused(func, fa, tm, grid, p->stream));
 #ifdef FUSED_PROF
@@ -627,9 +644,18 @@ extern "C" int fftb200_plan_create(fftb200_plan** out, const fftb200_plan_desc* 
                 }
         }
         if (d->kind == FFTB200_R2C) {
-            p->work = (cd*)fftb200_malloc(sizeof(cd) * (size_t)p->m * (size_t)p->batch);
-            if (!p->work) { rc = -1; break; }
-            p->launches += 2;
+            const bool fused_r2c = p->passes.size() == 1 && p->passes[0].fused_lm && !getenv("FFTB200_NO_FUSED_R2C") &&
+                                   fused_r2c_func(p->passes[0].fused_lm, p->passes[0].fused_lr);
+            if (fused_r2c) {
+                // promotion and extraction happen inside the fused kernel (fft_fused.cuh, R2C)
+                if (cudaFuncSetAttribute(fused_r2c_func(p->passes[0].fused_lm, p->passes[0].fused_lr), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)FUSED_SMEM) != cudaSuccess) { rc = fail("cudaFuncSetAttribute failed"); break; }
+                p->desc += " [real in, half spectrum out, no promote / extract passes]";
+            } else {
+                p->work = (cd*)fftb200_malloc(sizeof(cd) * (size_t)p->m * (size_t)p->batch);
+                if (!p->work) { rc = -1; break; }
+                p->launches += 2;
+            }
         }
         if (d->kind == FFTB200_BLUESTEIN) {
             const size_t m = (size_t)p->m;
@@ -844,6 +870,10 @@ static int exec_range(fftb200_plan* p, const void* d_in, void* d_out, long long 
     const int inverse = p->dir > 0;
     if (p->kind == FFTB200_C2C) return enqueue_c2c(p, (const cd*)d_in, (cd*)d_out, inverse, nbatch);
     const size_t m = (size_t)p->m, n = (size_t)p->n, total = m * (size_t)nbatch;
+    if (p->kind == FFTB200_R2C && !p->work) {
+        if (nbatch <= 0) return 0;
+        return enqueue_fused(p, p->passes[0], (const cd*)d_in, (cd*)d_out, 0, nbatch, 1);
+    }
     if (p->kind == FFTB200_R2C) {
         r2c_promote_kernel<<<grid_for(total), 256, 0, p->stream>>>(p->work, (const double*)d_in, total);
         if (enqueue_c2c(p, p->work, p->work, 0, nbatch) != 0) return -1;
@@ -891,7 +921,9 @@ extern "C" int fftb200_plan_exec_host(fftb200_plan* p, const void* h_in, void* h
     if (!p || !h_in || !h_out) return fail("plan_exec_host: null argument");
     const size_t in_per = (p->kind == FFTB200_R2C ? sizeof(double) : sizeof(cd)) * (size_t)p->n;      // bytes / transform
     const size_t out_per = sizeof(cd) * (p->kind == FFTB200_R2C ? (size_t)(p->n / 2 + 1) : (size_t)p->n);
-    const size_t per = in_per > out_per ? in_per : out_per;
+    // the fused r2c kernel cannot run in place: its staging buffers hold the real input followed by the half spectra
+    const bool split = p->kind == FFTB200_R2C && !p->work;
+    const size_t per = split ? in_per + out_per + 16 : (in_per > out_per ? in_per : out_per);
     if (!p->d_ring[0]) {
         size_t target = 32u << 20;                       // bytes per chunk
         if (const char* e = getenv("FFTB200_CHUNK_MB")) target = (size_t)atol(e) << 20;
@@ -899,7 +931,7 @@ extern "C" int fftb200_plan_exec_host(fftb200_plan* p, const void* h_in, void* h
         if (cb < 1) cb = 1;
         if (cb > p->batch) cb = p->batch;
         for (int i = 0; i < fftb200_plan::NSTAGE; i++) {
-            p->d_ring[i] = (cd*)fftb200_malloc(per * (size_t)cb);
+            p->d_ring[i] = (cd*)fftb200_malloc(per * (size_t)cb + 512);
             if (!p->d_ring[i]) return -1;
             if (cudaEventCreateWithFlags(&p->ev_up[i], cudaEventDisableTiming) != cudaSuccess ||
                 cudaEventCreateWithFlags(&p->ev_run[i], cudaEventDisableTiming) != cudaSuccess ||
@@ -918,10 +950,11 @@ extern "C" int fftb200_plan_exec_host(fftb200_plan* p, const void* h_in, void* h
         CU(cudaMemcpyAsync(p->d_ring[r], src + (size_t)b0 * in_per, in_per * (size_t)nb, cudaMemcpyHostToDevice, p->s_up));
         CU(cudaEventRecord(p->ev_up[r], p->s_up));
         CU(cudaStreamWaitEvent(p->stream, p->ev_up[r], 0));
-        if (exec_range(p, p->d_ring[r], p->d_ring[r], nb) != 0) return -1;
+        char* const d_res = split ? (char*)p->d_ring[r] + ((in_per * (size_t)cb + 255) & ~(size_t)255) : (char*)p->d_ring[r];
+        if (exec_range(p, p->d_ring[r], d_res, nb) != 0) return -1;
         CU(cudaEventRecord(p->ev_run[r], p->stream));
         CU(cudaStreamWaitEvent(p->s_down, p->ev_run[r], 0));
-        CU(cudaMemcpyAsync(dst + (size_t)b0 * out_per, p->d_ring[r], out_per * (size_t)nb, cudaMemcpyDeviceToHost, p->s_down));
+        CU(cudaMemcpyAsync(dst + (size_t)b0 * out_per, d_res, out_per * (size_t)nb, cudaMemcpyDeviceToHost, p->s_down));
         CU(cudaEventRecord(p->ev_down[r], p->s_down));
     }
     CU(cudaStreamSynchronize(p->s_down));

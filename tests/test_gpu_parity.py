@@ -83,6 +83,26 @@ def test_r2c_parity(gpu, port, O, n):
     assert O.rel_l2(got, port.r2c(x)) <= TOL
 
 
+@pytest.mark.parametrize("n,batch", [(256, 9), (4096, 5), (1 << 13, 41), (1 << 15, 300), (1 << 16, 7), (1 << 18, 3), (1 << 20, 5)])
+def test_r2c_batched_engine_plan(gpu, port, O, n, batch):
+    """Batched r2c (the GPU batch API of SURVEY 8a8): N = 2^13 .. 2^20 run inside the fused kernel (real tile in,
+    bins 0 .. n/2 out, no promote / extract passes); smaller N through the promote - c2c - extract plan."""
+    import torch
+    L = gpu.lib
+    x = port.fill(47, 0, n * batch).real.copy().reshape(batch, n)
+    plan = gpu.engine_plan(n, batch, gpu.FFTB200_R2C)
+    xd = torch.from_numpy(x).cuda()
+    yd = torch.zeros((batch, n // 2 + 1), dtype=torch.complex128, device="cuda")
+    for _ in range(2):
+        assert L.fftb200_plan_exec(plan, xd.data_ptr(), yd.data_ptr()) == 0
+    rows = sorted({0, batch // 2, batch - 1})
+    want = np.stack([port.r2c(x[r]) for r in rows])
+    assert O.rel_l2(yd[rows].cpu().numpy(), want) <= TOL
+    full = np.fft.rfft(x, axis=1)   # every row, against the accurate transform (the reference is 1e-11 away from it at 2^20)
+    assert O.rel_l2(yd.cpu().numpy(), full) <= 5e-11
+    L.fftb200_plan_destroy(plan)
+
+
 @pytest.mark.parametrize("key", sorted(k for k in GOLD.files if k.startswith("full_")))
 def test_golden_full_through_fft_auto(gpu, port, O, key):
     _, n, seed, tag = key.split("_")
