@@ -128,18 +128,25 @@ __global__ void __launch_bounds__(2 * PIPE_GROUP, 1) fft_pipe_kernel(const PipeA
     const int first = blockIdx.x, stride = gridDim.x;
     const int my_tiles = first < a.ntiles ? (int)((a.ntiles - first + stride - 1) / stride) : 0;
 
-    auto issue = [&](int k, int b) {  // one thread: start the load of this CTA's k-th tile into buffer b
+    // Barriers: buffer b is filled for tiles b, b + 3, b + 6, ... which the two groups consume alternately, and the load
+    // of tile k + 3 is issued by the group that consumed tile k - not by the group that will wait for it. With ONE barrier
+    // per buffer a group that is early could test the parity of a phase whose predecessor has not completed yet (the
+    // parity wait then passes on the phase before: stale data, a second expect_tx in the same phase and a launch failure;
+    // seen on the B200 about once per 10^7 tiles). So each buffer has TWO barriers used in turn (bar = b + 3 * (round & 1),
+    // parity (round >> 1) & 1): all phases of one barrier are waited for by the same group, in program order.
+    auto issue = [&](int k, int b, uint32_t rnd) {  // one thread: start the load of this CTA's k-th tile into buffer b
         const long long tile = first + (long long)k * stride;
         long long nvalid = a.batch - tile * NT;
         if (nvalid > NT) nvalid = NT;
         const uint32_t bytes = (uint32_t)nvalid * N * (uint32_t)sizeof(cd);
-        mbar_expect_tx(&full[b], bytes);
-        bulk_load(bufs + (size_t)b * PIPE_TILE, a.in + tile * PIPE_TILE, bytes, &full[b]);
+        uint64_t* const bar = &full[b + PIPE_STAGES * (rnd & 1)];
+        mbar_expect_tx(bar, bytes);
+        bulk_load(bufs + (size_t)b * PIPE_TILE, a.in + tile * PIPE_TILE, bytes, bar);
     };
 
     if (threadIdx.x == 0) {
 #pragma unroll
-        for (int b = 0; b < PIPE_STAGES; b++) mbar_init(&full[b], 1);
+        for (int b = 0; b < 2 * PIPE_STAGES; b++) mbar_init(&full[b], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
@@ -152,7 +159,7 @@ __global__ void __launch_bounds__(2 * PIPE_GROUP, 1) fft_pipe_kernel(const PipeA
     }
     __syncthreads();
     if (threadIdx.x == 0) {
-        for (int k = 0; k < PIPE_STAGES && k < my_tiles; k++) issue(k, k);
+        for (int k = 0; k < PIPE_STAGES && k < my_tiles; k++) issue(k, k, 0);
     }
 
     // thread-constant butterfly coordinates of the two radix-16 sub-passes
@@ -174,7 +181,7 @@ __global__ void __launch_bounds__(2 * PIPE_GROUP, 1) fft_pipe_kernel(const PipeA
     uint32_t round = 0;        // k / PIPE_STAGES
     for (int k = g; k < my_tiles; k += 2) {
         cd* const sm = bufs + (size_t)b * PIPE_TILE;
-        mbar_wait(&full[b], round & 1);
+        mbar_wait(&full[b + PIPE_STAGES * (round & 1)], (round >> 1) & 1);
         cd x[16];
         // ---- sub-pass 0: radix R0, exact constants, in place (each thread owns idx = t + 256 e) ----
 #pragma unroll
@@ -209,7 +216,7 @@ __global__ void __launch_bounds__(2 * PIPE_GROUP, 1) fft_pipe_kernel(const PipeA
         group_sync(g);  // the buffer is free: refill it with this CTA's tile k + 3
         if (t == 0 && k + PIPE_STAGES < my_tiles) {
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            issue(k + PIPE_STAGES, b);
+            issue(k + PIPE_STAGES, b, round + 1);
         }
         {
             constexpr double C8 = 0.70710678118654752440, C16 = 0.92387953251128675613, S16 = 0.38268343236508977173;
