@@ -16,7 +16,7 @@ LIB_PATH = os.environ.get("FFTB200_LIB") or os.path.join(_HERE, "lib", "libfft_b
 FFT_FORWARD, FFT_INVERSE = -1, 1
 FFT_GPU_CUDA, FFT_GPU_AUTO = 1, -1
 FFT_ESTIMATE, FFT_PREFER_GPU = 0, 1 << 9
-FFTB200_C2C, FFTB200_BLUESTEIN, FFTB200_R2C = 0, 1, 2
+FFTB200_C2C, FFTB200_BLUESTEIN, FFTB200_R2C, FFTB200_C2R = 0, 1, 2, 3
 
 _vp, _dp = C.c_void_p, C.POINTER(C.c_double)
 
@@ -90,6 +90,9 @@ _SIGS = {
     "fftb200_timer_start": (C.c_int, [_vp]),
     "fftb200_timer_stop": (C.c_int, [_vp, C.POINTER(C.c_float)]),
     "fftb200_pointwise_mul": (C.c_int, [_vp, _vp, _vp, C.c_size_t]),
+    "fftb200_pointwise_mul_conj": (C.c_int, [_vp, _vp, _vp, C.c_size_t]),
+    "fftb200_plan_set_stream": (C.c_int, [_vp, _vp]),
+    "fftb200_transpose": (C.c_int, [_vp, _vp, C.c_longlong, C.c_longlong, C.c_longlong, _vp]),
     "fftb200_plan_create_partial": (C.c_int, [C.POINTER(_vp), _vp, C.c_int, C.c_int, C.c_int, C.c_double]),
     "fftb200_permute_bac": (C.c_int, [_vp, _vp, C.c_longlong, C.c_longlong, C.c_longlong, _vp]),
     "fftb200_plan_stream": (_vp, [_vp]),
@@ -110,6 +113,10 @@ _SIGS = {
     "fftb200_host_tables_release": (None, []),
     "fftb200_host_twiddles_dist": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_int]),
     "fftb200_shard_range": (C.c_int, [C.c_longlong, C.c_int, C.c_int, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]),
+    "fft_gpu_convolution": (C.c_int, [_vp, C.c_int, _vp, C.c_int, _vp]),
+    "fft_gpu_circular_convolution": (C.c_int, [_vp, _vp, C.c_int, _vp]),
+    "fft_gpu_cross_correlation": (C.c_int, [_vp, _vp, C.c_int, _vp]),
+    "fft_gpu_autocorrelation": (C.c_int, [_vp, C.c_int, _vp]),
 }
 EXPORTS = sorted(_SIGS)
 for _name, (_res, _args) in _SIGS.items():
@@ -172,6 +179,85 @@ def r2c(x):
     lib.fft_execute(plan)
     lib.fft_destroy_plan(plan)
     return out
+
+
+def c2r(half, n):
+    """fft_plan_c2r_1d + fft_execute: n/2+1 complex bins -> n reals (inverse of r2c, scaled 1/n)."""
+    half = np.ascontiguousarray(half, dtype=np.complex128)
+    assert half.size == n // 2 + 1
+    out = np.empty(n, dtype=np.float64)
+    plan = lib.fft_plan_c2r_1d(n, ptr(half), ptr(out), 0)
+    if not plan:
+        raise RuntimeError("fft_plan_c2r_1d failed: " + lib.fftb200_last_error().decode())
+    lib.fft_execute(plan)
+    lib.fft_destroy_plan(plan)
+    return out
+
+
+def fft2d(x, sign=-1, api="plan"):
+    """2-D transform of a (rows, cols) complex128 array through fft_plan_dft_2d + fft_execute (api="plan"),
+    fft_gpu_dft_2d (api="dft") or the device handle API fft_gpu_plan_2d / fft_gpu_execute (api="gpu")."""
+    x = np.ascontiguousarray(x, dtype=np.complex128)
+    rows, cols = x.shape
+    out = np.empty_like(x)
+    if api == "plan":
+        plan = lib.fft_plan_dft_2d(rows, cols, ptr(x), ptr(out), sign, 0)
+        if not plan:
+            raise RuntimeError("fft_plan_dft_2d failed: " + lib.fftb200_last_error().decode())
+        lib.fft_execute(plan)
+        lib.fft_destroy_plan(plan)
+    elif api == "dft":
+        if lib.fft_gpu_dft_2d(ptr(x), ptr(out), rows, cols, -1 if sign < 0 else 1) != 0:
+            raise RuntimeError("fft_gpu_dft_2d failed: " + lib.fftb200_last_error().decode())
+    else:
+        require_gpu()
+        plan = lib.fft_gpu_plan_2d(rows, cols, -1 if sign < 0 else 1)
+        mem = lib.fft_gpu_alloc(x.size)
+        if not plan or not mem:
+            raise RuntimeError("fft_gpu_plan_2d failed: " + lib.fftb200_last_error().decode())
+        lib.fft_gpu_copy_h2d(mem, ptr(x), x.size)
+        lib.fft_gpu_execute(plan, mem, mem)
+        lib.fft_gpu_copy_d2h(ptr(out), mem, x.size)
+        lib.fft_gpu_destroy_plan(plan)
+        lib.fft_gpu_free(mem)
+    return out
+
+
+def _pair(fn, x, y, n_out):
+    x = np.ascontiguousarray(x, dtype=np.complex128)
+    y = np.ascontiguousarray(y, dtype=np.complex128)
+    out = np.empty(n_out, dtype=np.complex128)
+    return x, y, out
+
+
+def convolution(x, h):
+    """fft_gpu_convolution: linear convolution, len(x) + len(h) - 1 samples."""
+    x, h, y = _pair(None, x, h, len(x) + len(h) - 1)
+    if lib.fft_gpu_convolution(ptr(x), x.size, ptr(h), h.size, ptr(y)) != 0:
+        raise RuntimeError("fft_gpu_convolution failed: " + lib.fftb200_last_error().decode())
+    return y
+
+
+def circular_convolution(x, h):
+    x, h, y = _pair(None, x, h, len(x))
+    if lib.fft_gpu_circular_convolution(ptr(x), ptr(h), x.size, ptr(y)) != 0:
+        raise RuntimeError("fft_gpu_circular_convolution failed: " + lib.fftb200_last_error().decode())
+    return y
+
+
+def cross_correlation(x, y):
+    x, y, r = _pair(None, x, y, len(x))
+    if lib.fft_gpu_cross_correlation(ptr(x), ptr(y), x.size, ptr(r)) != 0:
+        raise RuntimeError("fft_gpu_cross_correlation failed: " + lib.fftb200_last_error().decode())
+    return r
+
+
+def autocorrelation(x):
+    x = np.ascontiguousarray(x, dtype=np.complex128)
+    r = np.empty_like(x)
+    if lib.fft_gpu_autocorrelation(ptr(x), x.size, ptr(r)) != 0:
+        raise RuntimeError("fft_gpu_autocorrelation failed: " + lib.fftb200_last_error().decode())
+    return r
 
 
 class PlanDesc(C.Structure):

@@ -93,4 +93,56 @@ __global__ void r2c_extract_kernel(cd* out, const cd* work, size_t n, size_t nh,
     }
 }
 
+// c2r, first step: rebuild the full Hermitian spectrum of a real signal from bins 0 .. n/2 (the inverse of
+// r2c_extract: X[n - k] = conj(X[k])); the inverse c2c then runs on it with the reference's stage operators
+__global__ void c2r_expand_kernel(cd* work, const cd* in, size_t n, size_t nh, size_t total) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+        const size_t t = i / n, k = i - t * n;
+        cd v;
+        if (k < nh) v = in[t * nh + k];
+        else { v = in[t * nh + (n - k)]; v.y = -v.y; }
+        work[i] = v;
+    }
+}
+
+// c2r, last step: keep the real parts
+__global__ void c2r_real_kernel(double* out, const cd* work, size_t total) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) out[i] = work[i].x;
+}
+
+// y[i] = conj(a[i]) * b[i] (cross-spectrum of applications/power_spectrum.c:176-178)
+__global__ void pointwise_mul_conj_kernel(cd* y, const cd* a, const cd* b, size_t total) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) y[i] = cmul_conj(b[i], a[i]);
+}
+
+// dst[b][c][r] = src[b][r][c]: 32 x 32 tiles of 16-byte elements through shared memory (row of 33 elements: the
+// column reads of the second phase fall into different banks); both phases move 512 contiguous bytes per warp.
+// grid = (ceil(cols / 32), ceil(rows / 32), batch chunks), block = (32, 8).
+__global__ void transpose_kernel(cd* __restrict__ dst, const cd* __restrict__ src, long long rows, long long cols, long long batch) {
+    __shared__ cd tile[32][33];
+    for (long long b = blockIdx.z; b < batch; b += gridDim.z) {
+        const cd* s = src + b * rows * cols;
+        cd* d = dst + b * rows * cols;
+        for (long long r0 = (long long)blockIdx.y * 32; r0 < rows; r0 += (long long)gridDim.y * 32) {
+            const long long c = (long long)blockIdx.x * 32 + threadIdx.x;
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+                const long long r = r0 + threadIdx.y + j;
+                if (r < rows && c < cols) tile[threadIdx.y + j][threadIdx.x] = s[r * cols + c];
+            }
+            __syncthreads();
+            const long long r = r0 + threadIdx.x;
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+                const long long cc = (long long)blockIdx.x * 32 + threadIdx.y + j;
+                if (r < rows && cc < cols) d[cc * rows + r] = tile[threadIdx.x][threadIdx.y + j];
+            }
+            __syncthreads();
+        }
+    }
+}
+
 }  // namespace fftb200

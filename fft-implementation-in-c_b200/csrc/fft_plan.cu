@@ -220,6 +220,7 @@ struct fftb200_plan {
     int ring_batch = 0;                                  // transforms per staging buffer
     cudaEvent_t ev_up[NSTAGE] = {}, ev_run[NSTAGE] = {}, ev_down[NSTAGE] = {};
     cudaStream_t stream = nullptr, s_up = nullptr, s_down = nullptr;
+    bool owns_stream = true;   // false after fftb200_plan_set_stream (plans chained on one stream, e.g. the two halves of a 2-D transform)
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     int launches = 0;
     std::string desc;
@@ -606,7 +607,8 @@ extern "C" int fftb200_plan_create(fftb200_plan** out, const fftb200_plan_desc* 
     const bool pow2 = (d->n & (d->n - 1)) == 0;
     int rc = 0;
     do {
-        if (d->kind == FFTB200_C2C || d->kind == FFTB200_R2C) {
+        if (d->kind == FFTB200_C2C || d->kind == FFTB200_R2C || d->kind == FFTB200_C2R) {
+            if (d->kind == FFTB200_C2R && d->direction != 1) { rc = fail("plan_create: a c2r plan is an inverse transform (direction +1)"); break; }
             if (!pow2) { rc = fail("plan_create: kind %d needs a power-of-two n (got %d)", d->kind, d->n); break; }
             p->m = d->n;
         } else if (d->kind == FFTB200_BLUESTEIN) {
@@ -625,7 +627,7 @@ extern "C" int fftb200_plan_create(fftb200_plan** out, const fftb200_plan_desc* 
         if ((rc = upload_table(p, ds, d, p->m)) != 0) break;
         if ((rc = upload_accurate(p, ds, d)) != 0) break;
         char head[96];
-        snprintf(head, sizeof(head), "%s n=%d b=%d dir=%d: ", d->kind == FFTB200_C2C ? "c2c" : d->kind == FFTB200_R2C ? "r2c" : "bluestein", d->n, d->batch, d->direction);
+        snprintf(head, sizeof(head), "%s n=%d b=%d dir=%d: ", d->kind == FFTB200_C2C ? "c2c" : d->kind == FFTB200_R2C ? "r2c" : d->kind == FFTB200_C2R ? "c2r" : "bluestein", d->n, d->batch, d->direction);
         p->desc = head;
         if ((rc = build_passes(p, ds)) != 0) break;
         p->launches = (int)p->passes.size();
@@ -656,6 +658,13 @@ extern "C" int fftb200_plan_create(fftb200_plan** out, const fftb200_plan_desc* 
                 if (!p->work) { rc = -1; break; }
                 p->launches += 2;
             }
+        }
+        if (d->kind == FFTB200_C2R) {
+            // Hermitian extension -> inverse c2c of the full length with the reference's stage operators -> real parts
+            p->work = (cd*)fftb200_malloc(sizeof(cd) * (size_t)p->m * (size_t)p->batch);
+            if (!p->work) { rc = -1; break; }
+            p->launches += 2;
+            p->desc += " [hermitian extension + inverse c2c + real parts]";
         }
         if (d->kind == FFTB200_BLUESTEIN) {
             const size_t m = (size_t)p->m;
@@ -870,6 +879,15 @@ static int exec_range(fftb200_plan* p, const void* d_in, void* d_out, long long 
     const int inverse = p->dir > 0;
     if (p->kind == FFTB200_C2C) return enqueue_c2c(p, (const cd*)d_in, (cd*)d_out, inverse, nbatch);
     const size_t m = (size_t)p->m, n = (size_t)p->n, total = m * (size_t)nbatch;
+    if (p->kind == FFTB200_C2R) {
+        if (nbatch <= 0) return 0;
+        const size_t nh = n / 2 + 1;
+        c2r_expand_kernel<<<grid_for(total), 256, 0, p->stream>>>(p->work, (const cd*)d_in, n, nh, total);
+        if (enqueue_c2c(p, p->work, p->work, 1, nbatch) != 0) return -1;
+        c2r_real_kernel<<<grid_for(total), 256, 0, p->stream>>>((double*)d_out, p->work, total);
+        CU(cudaGetLastError());
+        return 0;
+    }
     if (p->kind == FFTB200_R2C && !p->work) {
         if (nbatch <= 0) return 0;
         return enqueue_fused(p, p->passes[0], (const cd*)d_in, (cd*)d_out, 0, nbatch, 1);
@@ -919,8 +937,9 @@ extern "C" int fftb200_plan_exec(fftb200_plan* p, const void* d_in, void* d_out)
 // instead of their sum; pageable memory works too but serialises inside the driver.
 extern "C" int fftb200_plan_exec_host(fftb200_plan* p, const void* h_in, void* h_out) {
     if (!p || !h_in || !h_out) return fail("plan_exec_host: null argument");
-    const size_t in_per = (p->kind == FFTB200_R2C ? sizeof(double) : sizeof(cd)) * (size_t)p->n;      // bytes / transform
-    const size_t out_per = sizeof(cd) * (p->kind == FFTB200_R2C ? (size_t)(p->n / 2 + 1) : (size_t)p->n);
+    const size_t half = sizeof(cd) * (size_t)(p->n / 2 + 1);
+    const size_t in_per = p->kind == FFTB200_R2C ? sizeof(double) * (size_t)p->n : p->kind == FFTB200_C2R ? half : sizeof(cd) * (size_t)p->n;  // bytes / transform
+    const size_t out_per = p->kind == FFTB200_R2C ? half : p->kind == FFTB200_C2R ? sizeof(double) * (size_t)p->n : sizeof(cd) * (size_t)p->n;
     // the fused r2c kernel cannot run in place: its staging buffers hold the real input followed by the half spectra
     const bool split = p->kind == FFTB200_R2C && !p->work;
     const size_t per = split ? in_per + out_per + 16 : (in_per > out_per ? in_per : out_per);
@@ -981,7 +1000,7 @@ extern "C" void fftb200_plan_destroy(fftb200_plan* p) {
     }
     if (p->ev0) cudaEventDestroy(p->ev0);
     if (p->ev1) cudaEventDestroy(p->ev1);
-    if (p->stream) cudaStreamDestroy(p->stream);
+    if (p->stream && p->owns_stream) cudaStreamDestroy(p->stream);
     if (p->s_up) cudaStreamDestroy(p->s_up);
     if (p->s_down) cudaStreamDestroy(p->s_down);
     delete p;
@@ -989,6 +1008,34 @@ extern "C" void fftb200_plan_destroy(fftb200_plan* p) {
 
 extern "C" int fftb200_plan_launches(const fftb200_plan* p) { return p ? p->launches : 0; }
 extern "C" const char* fftb200_plan_describe(const fftb200_plan* p) { return p ? p->desc.c_str() : ""; }
+
+extern "C" int fftb200_plan_set_stream(fftb200_plan* p, void* stream) {
+    if (!p || !stream) return fail("plan_set_stream: null argument");
+    if (p->stream) CU(cudaStreamSynchronize(p->stream));
+    if (p->stream && p->owns_stream) cudaStreamDestroy(p->stream);
+    p->stream = (cudaStream_t)stream;
+    p->owns_stream = false;
+    return 0;
+}
+
+extern "C" int fftb200_transpose(void* dst, const void* src, long long rows, long long cols, long long batch, void* stream) {
+    if (!dst || !src || rows < 1 || cols < 1 || batch < 1 || dst == src) return fail("transpose: bad argument");
+    const long long gx = (cols + 31) / 32, gy = (rows + 31) / 32;
+    if (gx > 0x7fffffffLL) return fail("transpose: too many columns");
+    const dim3 grid((unsigned)gx, (unsigned)(gy > 65535 ? 65535 : gy), (unsigned)(batch > 65535 ? 65535 : batch));
+    transpose_kernel<<<grid, dim3(32, 8), 0, (cudaStream_t)stream>>>((cd*)dst, (const cd*)src, rows, cols, batch);
+    CU(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int fftb200_pointwise_mul_conj(void* y, const void* a, const void* b, size_t count) {
+    if (!y || !a || !b) return fail("pointwise_mul_conj: null argument");
+    if (count == 0) return 0;
+    pointwise_mul_conj_kernel<<<grid_for(count), 256>>>((cd*)y, (const cd*)a, (const cd*)b, count);
+    CU(cudaGetLastError());
+    CU(cudaDeviceSynchronize());
+    return 0;
+}
 
 extern "C" int fftb200_timer_start(fftb200_plan* p) {
     if (!p) return fail("timer: null plan");

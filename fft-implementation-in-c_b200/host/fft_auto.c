@@ -25,10 +25,15 @@ struct fft_plan {
     complex_t* in;   /* borrowed */
     complex_t* out;  /* borrowed */
     double* real_in; /* borrowed, r2c only */
+    double* real_out; /* borrowed, c2r only */
     fft_direction dir;
     unsigned flags;
     int kind;
     fftb200_plan* engine;
+    /* 2-D plans (fft_plan_dft_2d): a device-resident image and the 2-D plan of the device API */
+    int rows, cols;
+    fft_gpu_plan_t plan2d;
+    fft_gpu_memory_t image;
 };
 
 static int g_num_threads = 0;
@@ -57,6 +62,18 @@ fft_plan_t fft_plan_r2c_1d(int n, double* in, complex_t* out, unsigned flags) {
 
 void fft_execute(fft_plan_t plan) {
     if (!plan) return;
+    if (plan->plan2d) { /* host -> device, rows + columns on the device, device -> host (fft_auto.c:278-280) */
+        const size_t total = (size_t)plan->rows * (size_t)plan->cols;
+        fft_gpu_copy_h2d(plan->image, plan->in, total);
+        fft_gpu_execute(plan->plan2d, plan->image, plan->image);
+        fft_gpu_copy_d2h(plan->out, plan->image, total);
+        return;
+    }
+    if (plan->kind == FFTB200_C2R) {
+        if (fftb200_plan_exec_host(plan->engine, plan->in, plan->real_out) != 0)
+            fprintf(stderr, "fft_execute: %s\n", fftb200_last_error());
+        return;
+    }
     const void* src = plan->kind == FFTB200_R2C ? (const void*)plan->real_in : (const void*)plan->in;
     if (fftb200_plan_exec_host(plan->engine, src, plan->out) != 0)
         fprintf(stderr, "fft_execute: %s\n", fftb200_last_error());
@@ -67,15 +84,19 @@ void fft_execute_dft(fft_plan_t plan, complex_t* in, complex_t* out) {
     complex_t* keep_in = plan->in;
     complex_t* keep_out = plan->out;
     double* keep_real = plan->real_in;
+    double* keep_real_out = plan->real_out;
     plan->in = in; plan->out = out;
     if (plan->kind == FFTB200_R2C) plan->real_in = (double*)in;
+    if (plan->kind == FFTB200_C2R) plan->real_out = (double*)out;
     fft_execute(plan);
-    plan->in = keep_in; plan->out = keep_out; plan->real_in = keep_real;
+    plan->in = keep_in; plan->out = keep_out; plan->real_in = keep_real; plan->real_out = keep_real_out;
 }
 
 void fft_destroy_plan(fft_plan_t plan) {
     if (!plan) return;
     fftb200_plan_destroy(plan->engine);
+    fft_gpu_destroy_plan(plan->plan2d);
+    fft_gpu_free(plan->image);
     free(plan);
 }
 
@@ -88,14 +109,29 @@ int fft_auto(complex_t* in, complex_t* out, int n, int sign) {
     return fftb200_host_exec_cached(in, out, n, 1, sign < 0 ? -1 : 1, is_power_of_two(n) ? FFTB200_C2C : FFTB200_BLUESTEIN);
 }
 
-/* stubs in the reference (fft_auto.c:405-415) */
+/* Stubs in the reference (fft_auto.c:405-415 return NULL); implemented here with the contracts of its header.
+ * c2r (fft_auto.h:99-107): n/2 + 1 complex bins in, n reals out = the inverse of fft_plan_r2c_1d, scaled by 1/n like
+ * every inverse of the library. `in` is read when the plan is executed. */
 fft_plan_t fft_plan_c2r_1d(int n, complex_t* in, double* out, unsigned flags) {
-    (void)n; (void)in; (void)out; (void)flags;
-    return NULL;
+    if (n <= 0 || !in || !out) return NULL;
+    if (!is_power_of_two(n)) return NULL;
+    fft_plan_t p = make_plan(n, in, NULL, NULL, 1, flags | FFT_REAL_OUTPUT, FFTB200_C2R);
+    if (p) p->real_out = out;
+    return p;
 }
+/* 2-D (fft_auto.h:109-121): row-major rows x cols, rows then columns (applications/image_fft.c:35-72); sign < 0
+ * forward, otherwise inverse scaled by 1/(rows*cols). in/out are borrowed and may alias. */
 fft_plan_t fft_plan_dft_2d(int rows, int cols, complex_t* in, complex_t* out, int sign, unsigned flags) {
-    (void)rows; (void)cols; (void)in; (void)out; (void)sign; (void)flags;
-    return NULL;
+    if (rows <= 0 || cols <= 0 || !in || !out) return NULL;
+    fft_plan_t p = (fft_plan_t)calloc(1, sizeof(struct fft_plan));
+    if (!p) return NULL;
+    p->n = rows * cols; p->rows = rows; p->cols = cols; p->in = in; p->out = out;
+    p->dir = sign < 0 ? FFT_FORWARD : FFT_INVERSE;
+    p->flags = flags; p->kind = FFTB200_C2C;
+    p->plan2d = fft_gpu_plan_2d(rows, cols, p->dir);
+    p->image = p->plan2d ? fft_gpu_alloc((size_t)rows * (size_t)cols) : NULL;
+    if (!p->plan2d || !p->image) { fft_destroy_plan(p); return NULL; }
+    return p;
 }
 
 char* fft_export_wisdom_to_string(void) { return strdup("# FFT Wisdom v2.0.0\n"); }

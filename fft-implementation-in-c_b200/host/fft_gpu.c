@@ -20,8 +20,12 @@ struct fft_gpu_memory {
 };
 
 struct fft_gpu_plan {
-    fftb200_plan* engine;
-    int n, batch;
+    fftb200_plan* engine;  /* 1-D: the batched plan. 2-D: the row pass (n = cols, batch = rows)                      */
+    fftb200_plan* engine2; /* 2-D: the column pass, chained on the row pass's stream (NULL for 1-D plans)          */
+    void* scratch;         /* 2-D through corner turns: rows * cols complex                                         */
+    int n, batch;          /* 1-D shape; for 2-D plans n * batch = rows * cols                                      */
+    int rows, cols;        /* 2-D shape, 0 for 1-D plans                                                            */
+    int turn;              /* 2-D: 1 = transpose, contiguous column transforms, transpose back; 0 = strided kernels */
     fft_direction direction;
 };
 
@@ -113,22 +117,45 @@ fft_gpu_plan_t fft_gpu_plan_1d(int n, int batch, fft_direction direction) {
     if (n <= 0 || batch <= 0) return NULL;
     fft_gpu_plan_t p = (fft_gpu_plan_t)malloc(sizeof(*p));
     if (!p) return NULL;
+    memset(p, 0, sizeof(*p));
     p->engine = fftb200_host_make_plan(n, batch, (int)direction, is_power_of_two(n) ? FFTB200_C2C : FFTB200_BLUESTEIN);
     if (!p->engine) { free(p); return NULL; }
     p->n = n; p->batch = batch; p->direction = direction;
     return p;
 }
 
+/* 2-D execution on device pointers: rows first, then columns (the decomposition of the reference's CPU code,
+ * applications/image_fft.c:35-72), everything enqueued on one stream and synchronised once. */
+static int execute_2d(fft_gpu_plan_t plan, void* in, void* out) {
+    void* st = fftb200_plan_stream(plan->engine);
+    if (fftb200_plan_exec_async(plan->engine, in, out) != 0) return -1;
+    if (!plan->turn) {
+        if (fftb200_plan_exec_async(plan->engine2, out, out) != 0) return -1;
+    } else {
+        if (fftb200_transpose(plan->scratch, out, plan->rows, plan->cols, 1, st) != 0) return -1;
+        if (fftb200_plan_exec_async(plan->engine2, plan->scratch, plan->scratch) != 0) return -1;
+        if (fftb200_transpose(out, plan->scratch, plan->cols, plan->rows, 1, st) != 0) return -1;
+    }
+    return fftb200_plan_sync(plan->engine);
+}
+
 void fft_gpu_execute(fft_gpu_plan_t plan, fft_gpu_memory_t in, fft_gpu_memory_t out) {
     if (!plan || !in || !out) return;
     const size_t need = (size_t)plan->n * (size_t)plan->batch;
     if (in->size < need || out->size < need) { fprintf(stderr, "fft_gpu: execute: buffer smaller than n*batch\n"); return; }
+    if (plan->engine2) {
+        if (execute_2d(plan, in->dptr, out->dptr) != 0) report("execute 2d");
+        return;
+    }
     if (fftb200_plan_exec(plan->engine, in->dptr, out->dptr) != 0) report("execute");
 }
 
 void fft_gpu_destroy_plan(fft_gpu_plan_t plan) {
     if (!plan) return;
+    if (plan->engine) fftb200_plan_sync(plan->engine);
+    fftb200_plan_destroy(plan->engine2); /* borrows the first plan's stream: goes first */
     fftb200_plan_destroy(plan->engine);
+    fftb200_free(plan->scratch);
     free(plan);
 }
 
@@ -171,14 +198,70 @@ int fft_gpu_dft_1d(complex_t* in, complex_t* out, int n, fft_direction direction
     return fft_gpu_dft_1d_batch(in, out, n, 1, direction);
 }
 
-/* 2-D: stubs in the reference (gpu/fft_gpu.c:377-394) */
-fft_gpu_plan_t fft_gpu_plan_2d(int rows, int cols, fft_direction direction) {
-    (void)rows; (void)cols; (void)direction;
-    return NULL;
+/* 2-D transforms of a row-major rows x cols array. Stubs in the reference (gpu/fft_gpu.c:377-394 return NULL / -1);
+ * built here from the batched 1-D kernels the way the reference's CPU code does it (applications/image_fft.c:35-72:
+ * every row, then every column), forward unscaled, inverse scaled by 1/(rows*cols) ONCE (the reference's fft_2d
+ * scales the inverse twice, :63-71; the public headers promise 1/n). The row pass is one batched plan (n = cols,
+ * batch = rows). The column pass is
+ *   - for power-of-two shapes with >= 64 rows: stages 1 .. log2(rows) of a size rows*cols Stockham plan - exactly the
+ *     column transforms, in place, through the strided tile kernels (no transposes, twiddles = the reference's
+ *     size-`rows` tables); otherwise
+ *   - transpose, one batched plan (n = rows, batch = cols, Bluestein when rows is not a power of two), transpose back.
+ * A degenerate shape (one row or one column) is a 1-D plan. */
+static fftb200_plan* make_column_plan(int rows, int cols, int direction) {
+    if (!is_power_of_two(rows) || !is_power_of_two(cols) || rows < 64) return NULL;
+    fftb200_plan_desc d;
+    memset(&d, 0, sizeof(d));
+    d.n = rows * cols; d.batch = 1; d.direction = direction < 0 ? -1 : 1; d.kind = FFTB200_C2C;
+    d.table_n = rows;
+    d.twiddles = fftb200_host_twiddles(rows);
+    if (!d.twiddles) return NULL;
+    fftb200_plan* p = NULL;
+    if (fftb200_plan_create_partial(&p, &d, 0, log2_int(rows), 0, 1.0 / (double)rows) != 0) return NULL;
+    return p;
 }
+
+fft_gpu_plan_t fft_gpu_plan_2d(int rows, int cols, fft_direction direction) {
+    if (rows <= 0 || cols <= 0 || (long long)rows * cols > (1LL << 30)) return NULL;
+    if (rows == 1) return fft_gpu_plan_1d(cols, 1, direction);
+    if (cols == 1) return fft_gpu_plan_1d(rows, 1, direction);
+    const int dir = (int)direction < 0 ? -1 : 1;
+    fft_gpu_plan_t p = (fft_gpu_plan_t)malloc(sizeof(*p));
+    if (!p) return NULL;
+    memset(p, 0, sizeof(*p));
+    p->n = cols; p->batch = rows; p->rows = rows; p->cols = cols; p->direction = direction;
+    p->engine = fftb200_host_make_plan(cols, rows, dir, is_power_of_two(cols) ? FFTB200_C2C : FFTB200_BLUESTEIN);
+    if (!p->engine) { free(p); return NULL; }
+    if (!getenv("FFTB200_2D_TURN")) p->engine2 = make_column_plan(rows, cols, dir);
+    if (!p->engine2) {
+        p->turn = 1;
+        p->engine2 = fftb200_host_make_plan(rows, cols, dir, is_power_of_two(rows) ? FFTB200_C2C : FFTB200_BLUESTEIN);
+        p->scratch = fftb200_malloc(sizeof(complex_t) * (size_t)rows * (size_t)cols);
+    }
+    if (!p->engine2 || (p->turn && !p->scratch) ||
+        fftb200_plan_set_stream(p->engine2, fftb200_plan_stream(p->engine)) != 0) {
+        report("plan 2d");
+        fft_gpu_destroy_plan(p);
+        return NULL;
+    }
+    return p;
+}
+
 int fft_gpu_dft_2d(complex_t* in, complex_t* out, int rows, int cols, fft_direction direction) {
-    (void)in; (void)out; (void)rows; (void)cols; (void)direction;
-    return -1;
+    if (!in || !out || rows <= 0 || cols <= 0) return -1;
+    fft_gpu_plan_t p = fft_gpu_plan_2d(rows, cols, direction);
+    if (!p) return -1;
+    const size_t total = (size_t)rows * (size_t)cols;
+    int rc = -1;
+    fft_gpu_memory_t buf = fft_gpu_alloc(total);
+    if (buf && fftb200_memcpy_h2d(buf->dptr, in, total * sizeof(complex_t)) == 0) {
+        rc = p->engine2 ? execute_2d(p, buf->dptr, buf->dptr) : fftb200_plan_exec(p->engine, buf->dptr, buf->dptr);
+        if (rc == 0) rc = fftb200_memcpy_d2h(out, buf->dptr, total * sizeof(complex_t));
+    }
+    if (rc != 0) report("dft_2d");
+    fft_gpu_free(buf);
+    fft_gpu_destroy_plan(p);
+    return rc == 0 ? 0 : -1;
 }
 
 const char* fft_gpu_get_device_name(void) {

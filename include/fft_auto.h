@@ -42,9 +42,12 @@ int fft_auto(complex_t* in, complex_t* out, int n, int sign);
  * (which snapshots `in` at plan time and then frees the snapshot, fft_auto.c:391-403) the plan
  * reads `in` when it is executed. */
 fft_plan_t fft_plan_r2c_1d(int n, double* in, complex_t* out, unsigned flags);
-/* [107] stub in the reference (returns NULL); same here */
+/* [107] n/2 + 1 complex bins -> n reals (power-of-two n): the inverse of fft_plan_r2c_1d, scaled by 1/n. A stub in the
+ * reference (fft_auto.c:405-408 returns NULL); implemented here with the header's contract. `in` is read at execute time. */
 fft_plan_t fft_plan_c2r_1d(int n, complex_t* in, double* out, unsigned flags);
-/* [121] stub in the reference (returns NULL); same here */
+/* [121] 2-D transform of a row-major rows x cols array, rows then columns (the decomposition of the reference's CPU
+ * code, applications/image_fft.c:35-72); sign < 0 forward, otherwise inverse scaled by 1/(rows*cols). Any shape with
+ * rows*cols <= 2^30. A stub in the reference (fft_auto.c:411-415 returns NULL); implemented here. */
 fft_plan_t fft_plan_dft_2d(int rows, int cols, complex_t* in, complex_t* out, int sign, unsigned flags);
 
 /* [130, 137] */

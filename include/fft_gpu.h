@@ -46,7 +46,9 @@ void fft_gpu_destroy_plan(fft_gpu_plan_t plan); /* [108] */
 int fft_gpu_dft_1d(complex_t* in, complex_t* out, int n, fft_direction direction);
 int fft_gpu_dft_1d_batch(complex_t* in, complex_t* out, int n, int batch, fft_direction direction);
 
-/* [143, 154] stubs in the reference (NULL / -1); same here */
+/* [143, 154] 2-D plans over row-major rows x cols device buffers (execute with fft_gpu_execute, in place allowed) and
+ * the host-pointer one-shot. Stubs in the reference (gpu/fft_gpu.c:377-394: NULL / -1); implemented here: one batched
+ * row pass + strided column kernels (or two corner turns), forward unscaled, inverse scaled by 1/(rows*cols). */
 fft_gpu_plan_t fft_gpu_plan_2d(int rows, int cols, fft_direction direction);
 int fft_gpu_dft_2d(complex_t* in, complex_t* out, int rows, int cols, fft_direction direction);
 

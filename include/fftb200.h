@@ -30,7 +30,8 @@ typedef struct fftb200_plan fftb200_plan;
 enum fftb200_kind {
     FFTB200_C2C = 0,       /* power-of-two complex transform                                  */
     FFTB200_BLUESTEIN = 1, /* arbitrary n through a padded power-of-two circular convolution  */
-    FFTB200_R2C = 2        /* real input, n/2 + 1 complex outputs, power-of-two n             */
+    FFTB200_R2C = 2,       /* real input, n/2 + 1 complex outputs, power-of-two n             */
+    FFTB200_C2R = 3        /* n/2 + 1 complex bins in, n real outputs scaled by 1/n (direction +1) */
 };
 
 typedef struct fftb200_plan_desc {
@@ -72,8 +73,8 @@ int fftb200_fill_splitmix(void* dst, unsigned long long seed, unsigned long long
 
 /* ---- plans ---- */
 int fftb200_plan_create(fftb200_plan** out, const fftb200_plan_desc* desc);
-/* d_in / d_out are device pointers (complex; R2C: d_in is n*batch doubles, d_out (n/2+1)*batch complex).
- * In place (d_in == d_out) is allowed for C2C and BLUESTEIN. Returns after the result is visible. */
+/* d_in / d_out are device pointers (complex; R2C: d_in is n*batch doubles, d_out (n/2+1)*batch complex; C2R the
+ * other way round). In place (d_in == d_out) is allowed for C2C, BLUESTEIN and C2R. Returns after the result is visible. */
 int fftb200_plan_exec(fftb200_plan* plan, const void* d_in, void* d_out);
 /* Same, but only enqueues on the plan's stream. */
 int fftb200_plan_exec_async(fftb200_plan* plan, const void* d_in, void* d_out);
@@ -95,6 +96,13 @@ int fftb200_plan_create_partial(fftb200_plan** out, const fftb200_plan_desc* des
 /* dst[b][a][c] = src[a][b][c], complex elements, c contiguous; enqueued on `stream` (a cudaStream_t, may be NULL). */
 int fftb200_permute_bac(void* d_dst, const void* d_src, long long A, long long B, long long C, void* stream);
 void* fftb200_plan_stream(fftb200_plan* plan);   /* the plan's cudaStream_t */
+/* Chain a plan behind another one: from now on it enqueues on `stream` (a cudaStream_t owned by someone else, e.g.
+ * fftb200_plan_stream of the plan that runs before it), so no host synchronisation is needed between the two. */
+int fftb200_plan_set_stream(fftb200_plan* plan, void* stream);
+/* dst[b][c][r] = src[b][r][c], complex elements, enqueued on `stream`: the corner turn of the 2-D transform
+ * (rows then columns, the decomposition of applications/image_fft.c:35-72) when the columns are too short or too
+ * few for the strided column kernels. dst != src. */
+int fftb200_transpose(void* d_dst, const void* d_src, long long rows, long long cols, long long batch, void* stream);
 /* Fused exchange. A peer table holds the base pointers of one exchange buffer on all 2^log_world ranks as seen from
  * this process (own buffer and IPC-opened peers). With fftb200_plan_set_peer_output the last pass of a partial plan
  * stores over NVLink peer memory instead of into d_out: output index row * 2^log_width + col goes to rank
@@ -120,6 +128,8 @@ int fftb200_timer_stop(fftb200_plan* plan, float* elapsed_ms);   /* synchronises
 /* ---- elementwise helpers used by the callers either side of the transform ---- */
 /* y[i] = a[i] * b[i], count complex elements (FFT convolution, Bluestein's frequency-domain product) */
 int fftb200_pointwise_mul(void* d_y, const void* d_a, const void* d_b, size_t count);
+/* y[i] = conj(a[i]) * b[i] (cross-spectrum for FFT correlation, applications/power_spectrum.c:176-178) */
+int fftb200_pointwise_mul_conj(void* d_y, const void* d_a, const void* d_b, size_t count);
 
 const char* fftb200_last_error(void);
 

@@ -31,4 +31,13 @@ void fftb200_host_tables_release(void);
  * 2^(log_total - log_world) - 1 complex numbers. */
 int fftb200_host_twiddles_dist(double* out, int log_total, int log_world, int rank, int log_m);
 
+/* FFT convolution / correlation with host pointers (host/fft_apps.c): GPU versions of the reference's CPU callers
+ * applications/convolution.c:34-96 (fft_convolution: y has nx + nh - 1 samples; circular_convolution: n samples) and
+ * applications/power_spectrum.c:133-192 (autocorrelation_fft / cross_correlation_fft: the first n lags of
+ * IFFT(conj(X) * Y) over next_power_of_two(2n) points). 0 on success, -1 on bad arguments or without a GPU. */
+int fft_gpu_convolution(const complex_t* x, int nx, const complex_t* h, int nh, complex_t* y);
+int fft_gpu_circular_convolution(const complex_t* x, const complex_t* h, int n, complex_t* y);
+int fft_gpu_cross_correlation(const complex_t* x, const complex_t* y, int n, complex_t* ccf);
+int fft_gpu_autocorrelation(const complex_t* x, int n, complex_t* acf);
+
 #endif /* FFTB200_EXT_H */

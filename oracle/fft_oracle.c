@@ -187,6 +187,87 @@ int oracle_r2c(const double* in, double* out_half, int n) {
     return rc;
 }
 
+/* ---- the callers either side of the transform (SURVEY.md 8f "next" rows) ------------------------------- */
+
+/* c2r: the reference only declares it (fft_auto.h:99-107, stub at fft_auto.c:405-408). Defined here as the inverse
+ * of oracle_r2c in the reference's own arithmetic: rebuild the Hermitian spectrum X[n-k] = conj(X[k]) from bins
+ * 0 .. n/2, run the reference's inverse c2c (scaled 1/n, radix2_dit.c:115-119) and keep the real parts. */
+int oracle_c2r(const double* in_half, double* out, int n) {
+    if (n <= 0 || (n & (n - 1))) return -1;
+    const cplx* h = (const cplx*)in_half;
+    cplx* t = malloc((size_t)n * sizeof(cplx));
+    if (!t) return -1;
+    for (int k = 0; k < n; k++) t[k] = k <= n / 2 ? h[k] : conj(h[n - k]);
+    int rc = oracle_fft_pow2((double*)t, n, 1, 0);
+    if (rc == 0) for (int i = 0; i < n; i++) out[i] = creal(t[i]);
+    free(t);
+    return rc;
+}
+
+/* 2-D transform, row-column decomposition of applications/image_fft.c:35-72 on a row-major rows x cols array:
+ * every row, then every column, with the 1-D oracle. double_scale != 0 reproduces the reference's inverse, which
+ * divides by rows*cols a second time (:63-71) after each 1-D inverse already scaled; double_scale == 0 is the
+ * contract of the public headers (inverse scaled by 1/(rows*cols) once), which is what the product implements.
+ * quirk != 0 reproduces the reference's missing permutation when rows or cols is 4, 8 or 16 (see oracle_fft_pow2). */
+int oracle_fft2d(double* data, int rows, int cols, int dir, int double_scale, int quirk) {
+    if (rows <= 0 || cols <= 0 || (rows & (rows - 1)) || (cols & (cols - 1))) return -1;
+    cplx* x = (cplx*)data;
+    for (int i = 0; i < rows; i++) oracle_fft_pow2((double*)(x + (size_t)i * cols), cols, dir, quirk);   /* :41-43 */
+    cplx* col = malloc((size_t)rows * sizeof(cplx));
+    if (!col) return -1;
+    for (int j = 0; j < cols; j++) {                                                                  /* :46-60 */
+        for (int i = 0; i < rows; i++) col[i] = x[(size_t)i * cols + j];
+        oracle_fft_pow2((double*)col, rows, dir, quirk);
+        for (int i = 0; i < rows; i++) x[(size_t)i * cols + j] = col[i];
+    }
+    free(col);
+    if (dir > 0 && double_scale) {
+        double scale = 1.0 / (rows * cols);
+        for (size_t i = 0; i < (size_t)rows * cols; i++) x[i] *= scale;
+    }
+    return 0;
+}
+
+/* Shared body of the spectral-product callers: zero-pad a and b to n_fft, forward transforms, pointwise product
+ * (conj_a != 0: conj(A) * B), inverse transform, first n_out samples. */
+static int spectral_product(const cplx* a, int na, const cplx* b, int nb, int n_fft, int conj_a, cplx* out, int n_out) {
+    cplx* A = calloc((size_t)n_fft, sizeof(cplx));
+    cplx* B = calloc((size_t)n_fft, sizeof(cplx));
+    if (!A || !B) { free(A); free(B); return -1; }
+    memcpy(A, a, (size_t)na * sizeof(cplx));
+    memcpy(B, b, (size_t)nb * sizeof(cplx));
+    int rc = oracle_fft_auto((double*)A, (double*)A, n_fft, -1, 0);
+    if (rc == 0) rc = oracle_fft_auto((double*)B, (double*)B, n_fft, -1, 0);
+    if (rc == 0) {
+        for (int i = 0; i < n_fft; i++) A[i] = conj_a ? conj(A[i]) * B[i] : A[i] * B[i];
+        rc = oracle_fft_auto((double*)A, (double*)A, n_fft, 1, 0);
+    }
+    if (rc == 0) memcpy(out, A, (size_t)n_out * sizeof(cplx));
+    free(A); free(B);
+    return rc;
+}
+
+/* applications/convolution.c:34-66: linear convolution, y has nx + nh - 1 samples */
+int oracle_convolution(const double* x, int nx, const double* h, int nh, double* y) {
+    if (nx <= 0 || nh <= 0) return -1;
+    return spectral_product((const cplx*)x, nx, (const cplx*)h, nh, next_pow2(nx + nh - 1), 0, (cplx*)y, nx + nh - 1);
+}
+/* applications/convolution.c:71-96: circular convolution of two length-n signals (the reference needs a power of
+ * two; any n here, through the Bluestein oracle) */
+int oracle_circular_convolution(const double* x, const double* h, int n, double* y) {
+    if (n <= 0) return -1;
+    return spectral_product((const cplx*)x, n, (const cplx*)h, n, n, 0, (cplx*)y, n);
+}
+/* applications/power_spectrum.c:162-192: cross-correlation, conj(X) * Y, padded to next_pow2(2n), first n lags */
+int oracle_cross_correlation(const double* x, const double* y, int n, double* ccf) {
+    if (n <= 0) return -1;
+    return spectral_product((const cplx*)x, n, (const cplx*)y, n, next_pow2(2 * n), 1, (cplx*)ccf, n);
+}
+/* applications/power_spectrum.c:133-159: autocorrelation, X * conj(X) */
+int oracle_autocorrelation(const double* x, int n, double* acf) {
+    return oracle_cross_correlation(x, x, n, acf);
+}
+
 /* Independent O(n^2) truth for small n (algorithms/dft/naive_dft.c:55-97): used where the reference's
  * own FFT is wrong (N in {4, 8, 16}). Angles reduced with k*j mod n so it stays accurate. */
 void oracle_naive_dft(const double* ind, double* outd, int n, int dir) {

@@ -47,6 +47,12 @@ class Port:
         L.oracle_naive_dft.argtypes = [_dp, _dp, C.c_int, C.c_int]
         L.oracle_fill.argtypes = [_dp, C.c_uint64, C.c_uint64, C.c_uint64]
         L.oracle_fill.restype = None
+        L.oracle_c2r.argtypes = [_dp, _dp, C.c_int]
+        L.oracle_fft2d.argtypes = [_dp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
+        L.oracle_convolution.argtypes = [_dp, C.c_int, _dp, C.c_int, _dp]
+        L.oracle_circular_convolution.argtypes = [_dp, _dp, C.c_int, _dp]
+        L.oracle_cross_correlation.argtypes = [_dp, _dp, C.c_int, _dp]
+        L.oracle_autocorrelation.argtypes = [_dp, C.c_int, _dp]
 
     def fft(self, x, sign=-1, quirk=False):
         """fft_auto semantics on a 1-D complex128 array (any n): returns a new array."""
@@ -89,6 +95,46 @@ class Port:
         if self.lib.oracle_r2c(_ptr(x), _ptr(out.view(np.float64)), x.size) != 0:
             raise ValueError("oracle_r2c failed")
         return out
+
+    def c2r(self, half, n):
+        half = np.ascontiguousarray(half, dtype=np.complex128)
+        assert half.size == n // 2 + 1
+        out = np.empty(n, dtype=np.float64)
+        if self.lib.oracle_c2r(_ptr(half.view(np.float64)), _ptr(out), n) != 0:
+            raise ValueError("oracle_c2r failed")
+        return out
+
+    def fft2d(self, x, sign=-1, double_scale=False, quirk=False):
+        """Row-column 2-D transform of a (rows, cols) complex128 array (in a copy)."""
+        x = np.array(x, dtype=np.complex128, order="C", copy=True)
+        rows, cols = x.shape
+        if self.lib.oracle_fft2d(_ptr(x.view(np.float64)), rows, cols, -1 if sign < 0 else 1, int(double_scale), int(quirk)) != 0:
+            raise ValueError("oracle_fft2d: rows and cols must be powers of two")
+        return x
+
+    def convolution(self, x, h):
+        x = np.ascontiguousarray(x, dtype=np.complex128); h = np.ascontiguousarray(h, dtype=np.complex128)
+        y = np.empty(x.size + h.size - 1, dtype=np.complex128)
+        if self.lib.oracle_convolution(_ptr(x.view(np.float64)), x.size, _ptr(h.view(np.float64)), h.size, _ptr(y.view(np.float64))) != 0:
+            raise ValueError("oracle_convolution failed")
+        return y
+
+    def circular_convolution(self, x, h):
+        x = np.ascontiguousarray(x, dtype=np.complex128); h = np.ascontiguousarray(h, dtype=np.complex128)
+        y = np.empty_like(x)
+        if self.lib.oracle_circular_convolution(_ptr(x.view(np.float64)), _ptr(h.view(np.float64)), x.size, _ptr(y.view(np.float64))) != 0:
+            raise ValueError("oracle_circular_convolution failed")
+        return y
+
+    def cross_correlation(self, x, y):
+        x = np.ascontiguousarray(x, dtype=np.complex128); y = np.ascontiguousarray(y, dtype=np.complex128)
+        r = np.empty_like(x)
+        if self.lib.oracle_cross_correlation(_ptr(x.view(np.float64)), _ptr(y.view(np.float64)), x.size, _ptr(r.view(np.float64))) != 0:
+            raise ValueError("oracle_cross_correlation failed")
+        return r
+
+    def autocorrelation(self, x):
+        return self.cross_correlation(x, x)
 
     def naive_dft(self, x, sign=-1):
         x = np.ascontiguousarray(x, dtype=np.complex128)
@@ -158,7 +204,60 @@ class Par:
         self.lib.oracle_ref_four_step(_ptr(x.view(np.float64)), x.size, direction, threads)
 
 
+class Apps:
+    """The reference's FFT callers (applications/convolution.c, image_fft.c, power_spectrum.c), unmodified."""
+
+    def __init__(self):
+        path = os.path.join(_HERE, "_ref", "libappsref.so")
+        if not os.path.exists(path):
+            raise FileNotFoundError(path)
+        self.lib = L = C.CDLL(path)
+        L.oracle_ref_fft_convolution.argtypes = [_dp, C.c_int, _dp, C.c_int, _dp]
+        L.oracle_ref_circular_convolution.argtypes = [_dp, _dp, C.c_int, _dp]
+        L.oracle_ref_fft_2d.argtypes = [_dp, C.c_int, C.c_int, C.c_int]
+        L.oracle_ref_autocorrelation.argtypes = [_dp, C.c_int, _dp]
+        L.oracle_ref_cross_correlation.argtypes = [_dp, _dp, C.c_int, _dp]
+        for f in ("oracle_ref_fft_convolution", "oracle_ref_circular_convolution", "oracle_ref_fft_2d",
+                  "oracle_ref_autocorrelation", "oracle_ref_cross_correlation"):
+            getattr(L, f).restype = None
+
+    def convolution(self, x, h):
+        x = np.ascontiguousarray(x, dtype=np.complex128); h = np.ascontiguousarray(h, dtype=np.complex128)
+        y = np.empty(x.size + h.size - 1, dtype=np.complex128)
+        self.lib.oracle_ref_fft_convolution(_ptr(x.view(np.float64)), x.size, _ptr(h.view(np.float64)), h.size, _ptr(y.view(np.float64)))
+        return y
+
+    def circular_convolution(self, x, h):
+        x = np.ascontiguousarray(x, dtype=np.complex128); h = np.ascontiguousarray(h, dtype=np.complex128)
+        y = np.empty_like(x)
+        self.lib.oracle_ref_circular_convolution(_ptr(x.view(np.float64)), _ptr(h.view(np.float64)), x.size, _ptr(y.view(np.float64)))
+        return y
+
+    def fft2d(self, x, sign=-1):
+        x = np.array(x, dtype=np.complex128, order="C", copy=True)
+        self.lib.oracle_ref_fft_2d(_ptr(x.view(np.float64)), x.shape[0], x.shape[1], -1 if sign < 0 else 1)
+        return x
+
+    def cross_correlation(self, x, y):
+        x = np.ascontiguousarray(x, dtype=np.complex128); y = np.ascontiguousarray(y, dtype=np.complex128)
+        r = np.empty_like(x)
+        self.lib.oracle_ref_cross_correlation(_ptr(x.view(np.float64)), _ptr(y.view(np.float64)), x.size, _ptr(r.view(np.float64)))
+        return r
+
+    def autocorrelation(self, x):
+        x = np.ascontiguousarray(x, dtype=np.complex128)
+        r = np.empty_like(x)
+        self.lib.oracle_ref_autocorrelation(_ptr(x.view(np.float64)), x.size, _ptr(r.view(np.float64)))
+        return r
+
+
 _cache = {}
+
+
+def apps():
+    if "apps" not in _cache:
+        _cache["apps"] = Apps()
+    return _cache["apps"]
 
 
 def port():

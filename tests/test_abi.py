@@ -99,6 +99,17 @@ def test_no_cpu_fallback_without_gpu(F):
     assert not F.lib.fft_gpu_alloc(64)
     assert F.lib.fft_gpu_dft_1d_batch(F.ptr(x), F.ptr(y), 32, 2, -1) == -1
     assert F.lib.fft_gpu_init(F.FFT_GPU_AUTO) == -1
+    # the rows built on top of the hot path (c2r, 2-D, convolution / correlation) have no CPU fallback either
+    r = np.zeros(64)
+    assert not F.lib.fft_plan_c2r_1d(64, F.ptr(x), F.ptr(r), 0)
+    assert not F.lib.fft_plan_dft_2d(8, 8, F.ptr(x), F.ptr(y), -1, 0)
+    assert not F.lib.fft_gpu_plan_2d(8, 8, -1)
+    assert F.lib.fft_gpu_dft_2d(F.ptr(x), F.ptr(y), 8, 8, -1) == -1
+    assert F.lib.fft_gpu_convolution(F.ptr(x), 8, F.ptr(x), 8, F.ptr(y)) == -1
+    assert F.lib.fft_gpu_circular_convolution(F.ptr(x), F.ptr(x), 16, F.ptr(y)) == -1
+    assert F.lib.fft_gpu_cross_correlation(F.ptr(x), F.ptr(x), 16, F.ptr(y)) == -1
+    assert F.lib.fft_gpu_autocorrelation(F.ptr(x), 16, F.ptr(y)) == -1
+    assert not y.any()
     with pytest.raises(RuntimeError):
         F.require_gpu()
 
