@@ -66,7 +66,27 @@ def build(force=False, verbose=False):
     if jobs or not os.path.exists(LIB):
         run([NVCC, "-shared", "-o", LIB] + objs + ["-Xcompiler", "-fPIC", "-ccbin", "/usr/bin/g++",
                                                     "-lpthread", "-lm", "-cudart", "static"])
+    build_programs(force or bool(jobs))
     return LIB
+
+
+def build_programs(force=False):
+    """C99 callers of the public API (programs/*.c -> bin/): the reference's benchmark protocol and a tour of every entry
+    point. Plain gcc against include/ and the shared library, exactly how a user of the reference would build."""
+    if _VAR:
+        return
+    src_dir, bin_dir = os.path.join(HERE, "programs"), os.path.join(HERE, "bin")
+    os.makedirs(bin_dir, exist_ok=True)
+    for f in sorted(os.listdir(src_dir)):
+        if not f.endswith(".c"):
+            continue
+        src, exe = os.path.join(src_dir, f), os.path.join(bin_dir, f[:-2])
+        if force or _newer([src, LIB], exe):
+            r = subprocess.run([GCC, "-std=c99", "-O2", "-Wall", "-Wextra", "-I" + os.path.join(ROOT, "include"), src, "-o", exe,
+                                "-L" + os.path.dirname(LIB), "-lfft_b200", "-Wl,-rpath,$ORIGIN/../lib", "-lm"],
+                               capture_output=True, text=True)
+            if r.returncode != 0:
+                raise RuntimeError("build failed: " + f + "\n" + r.stderr)
 
 
 if __name__ == "__main__":

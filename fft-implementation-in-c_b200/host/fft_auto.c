@@ -134,8 +134,12 @@ fft_plan_t fft_plan_dft_2d(int rows, int cols, complex_t* in, complex_t* out, in
     return p;
 }
 
-char* fft_export_wisdom_to_string(void) { return strdup("# FFT Wisdom v2.0.0\n"); }
-int fft_import_wisdom_from_string(const char* wisdom) { return wisdom != NULL; }
+/* Wisdom: same header line as the reference's stub (fft_auto.c:417-421) followed by one line per planned shape; the
+ * importer pre-builds the host tables for those shapes (host/fft_gpu.c). 1 on success, 0 on failure (fft_auto.h:137). */
+char* fftb200_host_wisdom_export(void);            /* fft_gpu.c */
+int fftb200_host_wisdom_import(const char* wisdom); /* fft_gpu.c */
+char* fft_export_wisdom_to_string(void) { return fftb200_host_wisdom_export(); }
+int fft_import_wisdom_from_string(const char* wisdom) { return fftb200_host_wisdom_import(wisdom); }
 
 unsigned fft_get_hardware_capabilities(void) {
     unsigned caps = 0;

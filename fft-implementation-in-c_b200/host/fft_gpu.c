@@ -85,6 +85,55 @@ void fft_gpu_copy_d2h(complex_t* dst, fft_gpu_memory_t src, size_t size) {
     if (fftb200_memcpy_d2h(dst, src->dptr, size * sizeof(complex_t)) != 0) report("copy_d2h");
 }
 
+/* Wisdom (reference fft_auto.h:124-137; stubs in fft_auto.c:417-426): the planner here is a fixed function of
+ * (n, batch), so there is nothing to tune - what is worth carrying between processes is WHICH shapes were planned, so
+ * that an importer can build the host twiddle tables (the only expensive plan-time step: the reference's serial
+ * recurrence, n - 1 complex multiplies) before the first plan is asked for. One line per distinct shape. */
+#define WISDOM_MAX 128
+static struct { int n, batch, dir, kind; char desc[160]; } g_wisdom[WISDOM_MAX];
+static int g_wisdom_count = 0;
+static pthread_mutex_t g_wisdom_mu = PTHREAD_MUTEX_INITIALIZER;
+
+static void wisdom_note(int n, int batch, int dir, int kind, const char* desc) {
+    pthread_mutex_lock(&g_wisdom_mu);
+    int found = 0;
+    for (int i = 0; i < g_wisdom_count; i++)
+        if (g_wisdom[i].n == n && g_wisdom[i].batch == batch && g_wisdom[i].dir == dir && g_wisdom[i].kind == kind) found = 1;
+    if (!found && g_wisdom_count < WISDOM_MAX) {
+        g_wisdom[g_wisdom_count].n = n; g_wisdom[g_wisdom_count].batch = batch;
+        g_wisdom[g_wisdom_count].dir = dir; g_wisdom[g_wisdom_count].kind = kind;
+        snprintf(g_wisdom[g_wisdom_count].desc, sizeof(g_wisdom[0].desc), "%s", desc ? desc : "");
+        g_wisdom_count++;
+    }
+    pthread_mutex_unlock(&g_wisdom_mu);
+}
+
+char* fftb200_host_wisdom_export(void) {
+    pthread_mutex_lock(&g_wisdom_mu);
+    const size_t cap = 64 + (size_t)g_wisdom_count * 224;
+    char* out = (char*)malloc(cap);
+    if (out) {
+        size_t off = (size_t)snprintf(out, cap, "# FFT Wisdom v2.0.0\n");
+        for (int i = 0; i < g_wisdom_count && off < cap; i++)
+            off += (size_t)snprintf(out + off, cap - off, "plan %d %d %d %d # %s\n", g_wisdom[i].n, g_wisdom[i].batch, g_wisdom[i].dir,
+                                    g_wisdom[i].kind, g_wisdom[i].desc);
+    }
+    pthread_mutex_unlock(&g_wisdom_mu);
+    return out;
+}
+
+int fftb200_host_wisdom_import(const char* wisdom) {
+    if (!wisdom || strncmp(wisdom, "# FFT Wisdom", 12) != 0) return 0;
+    for (const char* line = wisdom; line && *line; line = strchr(line, '\n') ? strchr(line, '\n') + 1 : NULL) {
+        int n, batch, dir, kind;
+        if (sscanf(line, "plan %d %d %d %d", &n, &batch, &dir, &kind) != 4 || n <= 1) continue;
+        long long m = n;
+        if (kind == FFTB200_BLUESTEIN) { m = 1; while (m < 2LL * n - 1) m <<= 1; }
+        if ((m & (m - 1)) == 0 && m <= (1LL << 30)) (void)fftb200_host_twiddles((int)m);   /* cached per process */
+    }
+    return 1;
+}
+
 /* shared with fft_auto.c: build an engine plan of the given kind for (n, batch, direction) */
 fftb200_plan* fftb200_host_make_plan(int n, int batch, int direction, int kind) {
     if (n <= 0 || batch <= 0) return NULL;
@@ -109,6 +158,7 @@ fftb200_plan* fftb200_host_make_plan(int n, int batch, int direction, int kind) 
     d.twiddles_accurate = fftb200_host_twiddles_accurate(&d.accurate_n);
     fftb200_plan* p = NULL;
     if (!d.twiddles || fftb200_plan_create(&p, &d) != 0) { report("plan"); p = NULL; }
+    if (p) wisdom_note(n, batch, d.direction, kind, fftb200_plan_describe(p));
     free(chirp);
     return p;
 }

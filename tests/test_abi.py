@@ -87,6 +87,27 @@ int main(void) {
     assert r.returncode == 0, r.stdout + r.stderr
 
 
+def test_programs_build_and_refuse_to_run_on_the_cpu(F):
+    """programs/*.c (the reference's benchmark protocol, the API tour) are plain C99 callers of the public headers;
+    without a device they say so and exit 2 - they never compute on the CPU."""
+    bindir = os.path.join(ROOT, "fft-implementation-in-c_b200", "bin")
+    for name in ("demo_drop_in", "benchmark_all_gpu"):
+        exe = os.path.join(bindir, name)
+        assert os.path.exists(exe), exe
+        if F.lib.fft_gpu_available() == 1:
+            continue
+        r = subprocess.run([exe], capture_output=True, text=True)
+        assert r.returncode == 2 and "no CUDA device" in r.stdout
+
+
+def test_wisdom_header_and_import_contract(F):
+    import ctypes as C
+    p = F.lib.fft_export_wisdom_to_string()
+    assert C.string_at(p).decode().startswith("# FFT Wisdom v2.0.0\n")
+    assert F.lib.fft_import_wisdom_from_string(b"# FFT Wisdom v2.0.0\nplan 1024 1 -1 0 # x\n") == 1
+    assert F.lib.fft_import_wisdom_from_string(None) == 0
+
+
 def test_no_cpu_fallback_without_gpu(F):
     if F.lib.fft_gpu_available() == 1:
         pytest.skip("a GPU is visible: covered by the gpu suite")

@@ -145,3 +145,53 @@ def test_new_entry_points_reject_bad_arguments(gpu):
     assert L.fft_gpu_dft_2d(None, gpu.ptr(buf), 4, 4, -1) == -1
     assert L.fft_gpu_convolution(None, 4, gpu.ptr(buf), 4, gpu.ptr(buf)) == -1
     assert L.fft_gpu_cross_correlation(gpu.ptr(buf), gpu.ptr(buf), 0, gpu.ptr(buf)) == -1
+
+
+# ---- the callers: C programs written against the public headers, and the reference's own demo ----
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BIN = os.path.join(ROOT, "fft-implementation-in-c_b200", "bin")
+
+
+def _run(path, timeout=600):
+    import subprocess
+    assert os.path.exists(path), path + " is not built (python __graft_entry__.py)"
+    return subprocess.run([path], capture_output=True, text=True, timeout=timeout)
+
+
+def test_demo_drop_in_program(gpu):
+    r = _run(os.path.join(BIN, "demo_drop_in"))
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "all checks passed" in r.stdout and "FAILED" not in r.stdout
+
+
+def test_benchmark_program_follows_the_reference_protocol(gpu):
+    """benchmarks/benchmark_all.c protocol (sizes, iterations, rand() input, PASS iff reconstruction <= 1e-10)."""
+    r = _run(os.path.join(BIN, "benchmark_all_gpu"))
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "ALL ROWS PASS" in r.stdout
+    assert r.stdout.count("PASS (recon") == 8 * 3
+
+
+def test_reference_demo_runs_unmodified_on_this_library(gpu):
+    """examples/demo_v2_features.c of the reference, compiled with the reference's own headers (oracle/Makefile),
+    linked against libfft_b200.so: plans, fft_execute, fft_auto, the GPU demo and cleanup all go through the B200 path."""
+    exe = os.path.join(ROOT, "oracle", "_ref", "ref_demo_v2_features")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/ref_demo_v2_features not built (needs /root/reference at build time)")
+    r = _run(exe)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "GPU Device: NVIDIA" in r.stdout and "NVIDIA CUDA" in r.stdout
+    assert "No GPU available" not in r.stdout
+
+
+def test_wisdom_lists_planned_shapes_and_reimports(gpu):
+    L = gpu.lib
+    import ctypes as C
+    gpu.fft_auto(np.ones(2048, complex))
+    p = L.fft_export_wisdom_to_string()
+    text = C.string_at(p).decode()
+    assert text.startswith("# FFT Wisdom v2.0.0\n")          # the reference's header line (fft_auto.c:420)
+    assert "plan 2048 1 -1 0" in text
+    assert L.fft_import_wisdom_from_string(text.encode()) == 1
+    assert L.fft_import_wisdom_from_string(b"garbage") == 0
+    assert L.fft_import_wisdom_from_string(None) == 0
