@@ -51,6 +51,10 @@
 
 #include "fft_pipe.cuh"
 
+#ifndef FUSED_BDIRECT
+#define FUSED_BDIRECT 1
+#endif
+
 namespace fftb200 {
 
 struct FusedArgs {
@@ -313,6 +317,13 @@ fft_fused_kernel(const FusedArgs a, const __grid_constant__ CUtensorMap tm_in, c
     constexpr int LC = 12 - LM, LC2 = 12 - LR;          // log2 columns per A tile / k's per B tile
     constexpr int A3 = LM >= 9, B3 = LR >= 9;            // three sub-passes?
     constexpr int RA0 = A3 ? LM - 8 : LM - 4, RB0 = B3 ? LR - 8 : LR - 4;
+    // BDIRECT: pass-B results leave from registers (st.global, rows of C2 contiguous elements) instead of being staged in
+    // the ring buffer for a TMA store - nobody waits for them (no counter to publish) - and the buffer goes back to its
+    // manager as soon as the last gather has read it. That shortens a pass-B tile's buffer residency by a third but moves
+    // the store drain into the compute group's time. Same-box A/B at 2^28 points (ms, direct vs staged): 2^13 2.61 / 2.24,
+    // 2^14 2.34 / 2.62, 2^15 2.34 / 2.59, 2^16 2.35 / 2.26, 2^17 2.55 / 2.50, 2^18 3.04 / 2.77, 2^19 3.00 / 2.79,
+    // 2^20 3.39 / 2.95: it pays only for LR = 7 (rows of 32 elements, two sub-passes), which is where it is used.
+    constexpr bool BDIRECT = FUSED_BDIRECT && !COLS && !R2C && LR == 7;
 
     extern __shared__ __align__(128) unsigned char smem_raw[];
     cd* const bufs = reinterpret_cast<cd*>(smem_raw);
@@ -363,7 +374,7 @@ fft_fused_kernel(const FusedArgs a, const __grid_constant__ CUtensorMap tm_in, c
         auto load = [&](const FusedItem& x, auto waitq) {
             const int blk = (int)(x.tau & ((1 << LOG_TPT) - 1));
             const long long trg = x.tau >> LOG_TPT;
-            kinds[4 * w] = x.is_b; kinds[4 * w + 1] = blk; kinds[4 * w + 2] = x.g;
+            kinds[4 * w] = x.is_b; kinds[4 * w + 1] = blk; kinds[4 * w + 2] = x.g; kinds[4 * w + 3] = (int)trg;
             mbar_expect_tx(&full[w], (R2C && !x.is_b) ? PIPE_TILE * (uint32_t)sizeof(double) : PIPE_TILE * (uint32_t)sizeof(cd));
             if (x.is_b) {
                 asm volatile("fence.proxy.async;" ::: "memory");
@@ -440,7 +451,7 @@ fft_fused_kernel(const FusedArgs a, const __grid_constant__ CUtensorMap tm_in, c
                         else tma_store_2d(&tm_sc, 2 * (blk << LC), (int)((trl << LM) + q * (QT >> LC)), buf + q * QT, pol_last);
                         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                     }
-                } else {
+                } else if constexpr (!BDIRECT) {
                     const long long tr = (long long)cur_it.g * a.gt + trg;
 #pragma unroll
                     for (int q = 0; q < 4; q++) {
@@ -458,7 +469,8 @@ fft_fused_kernel(const FusedArgs a, const __grid_constant__ CUtensorMap tm_in, c
             // ---- next load, chasing the store quarter by quarter; then publish the store ----
             if (have) {
                 if (seen >= need) {
-                    load(it, storeq);
+                    if (BDIRECT && cur_it.is_b) load(it, nowaitq);   // nothing was stored from this buffer: it is free now
+                    else load(it, storeq);
 #ifdef FUSED_PROF
                     const long long m3 = clock64();
                     mp[2] += m3 - m2;
@@ -511,6 +523,7 @@ fft_fused_kernel(const FusedArgs a, const __grid_constant__ CUtensorMap tm_in, c
         pr_e += c1 - c0; pr_f += c2 - c1;
 #endif
         const int is_b = kinds[4 * b], kb = kinds[4 * b + 1];
+        const int kg = kinds[4 * b + 2], ktr = kinds[4 * b + 3];   // group and transform within it (read before the buffer is handed back)
         cd x[16];
         if (!is_b) {
             // ------------------------------ pass A: stages 1 .. LM over C = 2^LC columns ------------------------------
@@ -572,7 +585,7 @@ fft_fused_kernel(const FusedArgs a, const __grid_constant__ CUtensorMap tm_in, c
         } else {
             // ------------------------------ pass B: stages LM + 1 .. LM + LR for C2 = 2^LC2 values of k ------------------------------
             // the scratch block is in shared memory now: its ring slot may be overwritten (a completed read needs no fence)
-            if (t == 0 && !nowait) atomicAdd(a.flags + a.ngroups + kinds[4 * b + 2], 1);
+            if (t == 0 && !nowait) atomicAdd(a.flags + a.ngroups + kg, 1);
             if constexpr (COLS) {
                 // the tile is [t_lo][c16], the geometry of a pass-A tile; stages 9 .. 16 with T[8 + s][kb + 256 q]
                 typedef Geo<4, 8, 0, 0, 4, false> G0;
@@ -648,13 +661,25 @@ fft_fused_kernel(const FusedArgs a, const __grid_constant__ CUtensorMap tm_in, c
             typedef Geo<0, LR, LC2, AL, 4, true> GL;
             const GL gl(t);
             fused_gather<GL, SWL, 4, false>(x, sm, gl);
+            if constexpr (BDIRECT) fused_stage_done(&staged[b], t);   // this warp has read its part: the buffer goes back when all have
             {
                 cd tw[16];
                 fused_twiddles<4>(tw, a.tab + ((kb << LC2) + gl.hi + (gl.kloc << LM) - 1), LM + AL, a.dtw[2]);
                 SubStageGen<4, 1, 0, 0>::run(x, tw);
             }
-            group_sync(g2);   // every gather is done: stage X[k + M q] in place as [q][k], the box the tensor store expects
-            {
+            if constexpr (BDIRECT) {
+                // X[k + M q], k = (kb << LC2) + hi, q = kloc + (q' << AL): lanes run over hi first, so a warp instruction writes
+                // 32 / C2 rows of C2 contiguous elements (>= 64 bytes each)
+                const long long tr = (long long)kg * a.gt + ktr;
+                cd* p = a.out + ((size_t)tr << LOGN) + ((size_t)kb << LC2) + gl.hi + ((size_t)gl.kloc << LM);
+#pragma unroll
+                for (int q = 0; q < 16; q++) {
+                    cd r = x[q];
+                    if (INV) { r.x *= sc; r.y *= -sc; }
+                    p[(size_t)q << (AL + LM)] = r;
+                }
+            } else {
+                group_sync(g2);   // every gather is done: stage X[k + M q] in place as [q][k], the box the tensor store expects
                 cd* p = sm + gl.hi + (gl.kloc << LC2);
 #pragma unroll
                 for (int q = 0; q < 16; q++) {
@@ -662,8 +687,8 @@ fft_fused_kernel(const FusedArgs a, const __grid_constant__ CUtensorMap tm_in, c
                     if (INV) { r.x *= sc; r.y *= -sc; }
                     p[q << (AL + LC2)] = r;
                 }
+                fused_stage_done(&staged[b], t);
             }
-            fused_stage_done(&staged[b], t);
         }
         b += 2;
         if (b >= PIPE_STAGES) { b -= PIPE_STAGES; n++; }

@@ -32,6 +32,12 @@ __device__ __forceinline__ void tma_2d(void* dst, const CUtensorMap* tm, int c0,
                  : "memory");
 }
 
+__device__ __forceinline__ uint32_t mapa_u32(const double2* base, int peer, int elem) {
+    uint32_t local = s32(base + elem), remote;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local), "r"(peer));
+    return remote;
+}
+
 template <int MODE>
 __global__ void __launch_bounds__(THREADS, 1) gather_kernel(const __grid_constant__ CUtensorMap tm, const double2* in, double* sink, int C,
                                                             long long ntr) {
@@ -112,8 +118,8 @@ __global__ void __launch_bounds__(THREADS, 1) dsmem_kernel(double* sink, long lo
         for (int e = 0; e < TILE / THREADS; e++) {
             const int idx = threadIdx.x + e * THREADS;         // 0 .. 4095
             const int peer = idx / share, k = idx % share;
-            const double2* rp = cl.map_shared_rank(buf, peer) + r * share + k;
-            double2 v = *rp;
+            double2 v;
+            asm volatile("ld.shared::cluster.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(mapa_u32(buf, peer, r * share + ((k + it) & (share - 1)))));
             acc += v.x + v.y;
         }
     }
@@ -150,6 +156,7 @@ int main(int argc, char** argv) {
     for (int C : {1, 2, 4, 8, 16}) {
         int maxcl = 0;
         for (int mode = 0; mode < 3; mode++) {
+            if (getenv("CLBENCH_DSMEM_ONLY") && mode != 0) continue;
             auto kern = mode == 0 ? gather_kernel<0> : mode == 1 ? gather_kernel<1> : gather_kernel<2>;
             CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             if (C > 8) CK(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
