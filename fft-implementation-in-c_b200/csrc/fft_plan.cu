@@ -299,7 +299,8 @@ static int build_passes(fftb200_plan* p, DeviceState* ds) {
             return 0;
         }
     }
-    if (L >= 22 && L <= 25 && p->acc && !getenv("FFTB200_NO_FUSED") && !getenv("FFTB200_NO_FUSED_COLS") && !getenv("FFTB200_SPLIT")) {
+    // 2^21 (tail of 5 stages): pays from ~2^26 points per execution (x128: 4.19 vs 4.55 ms; x16 inside Bluestein 1.61 vs 1.57 ms)
+    if (L >= ((getenv("FFTB200_NO_L5") || p->batch < 32) ? 22 : 21) && L <= 25 && p->acc && !getenv("FFTB200_NO_FUSED") && !getenv("FFTB200_NO_FUSED_COLS") && !getenv("FFTB200_SPLIT")) {
         // stages 1 .. 16 in the fused kernel's column mode (intermediate in L2), then one LAST tile pass: two HBM round trips
         Pass fz;
         fz.k = nullptr; fz.fused_lm = 8; fz.fused_lr = 8; fz.fused_cols = 1;
