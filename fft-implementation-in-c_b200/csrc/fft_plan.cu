@@ -4,7 +4,12 @@
 // Replaces gpu/fft_cuda.cu of the reference (cuFFT wrapper, never built): plan = cufftPlanMany
 // (:138-163), exec = cufftExecZ2Z + device sync (:166-185), alloc/copies (:103-135).
 // There is no CPU fallback anywhere in this file: without a CUDA device every call fails.
+#ifndef _GNU_SOURCE
+#define _GNU_SOURCE
+#endif
 #include <cuda_runtime.h>
+#include <ctype.h>
+#include <sched.h>
 #include <stdarg.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -127,10 +132,50 @@ extern "C" void* fftb200_malloc(size_t bytes) {
     return p;
 }
 extern "C" void fftb200_free(void* p) { if (p) cudaFree(p); }
+// CPUs of the NUMA node the current device hangs off (sysfs local_cpulist of its PCI function); false when unknown.
+static bool device_local_cpus(cpu_set_t* set) {
+    int dev = 0;
+    char bus[32] = {0};
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetPCIBusId(bus, (int)sizeof(bus), dev) != cudaSuccess) { cudaGetLastError(); return false; }
+    for (char* c = bus; *c; c++) *c = (char)tolower((unsigned char)*c);
+    char path[128];
+    snprintf(path, sizeof(path), "/sys/bus/pci/devices/%s/local_cpulist", bus);
+    FILE* f = fopen(path, "r");
+    if (!f) return false;
+    char line[1024] = {0};
+    const bool ok = fgets(line, sizeof(line), f) != nullptr;
+    fclose(f);
+    if (!ok) return false;
+    CPU_ZERO(set);
+    int count = 0;
+    for (char* p = line; *p && *p != '\n';) {       // "0-15,32-47"
+        char* e;
+        long a = strtol(p, &e, 10), b = a;
+        if (e == p) break;
+        if (*e == '-') { p = e + 1; b = strtol(p, &e, 10); }
+        for (long c = a; c <= b && c < CPU_SETSIZE; c++) { CPU_SET((int)c, set); count++; }
+        p = (*e == ',') ? e + 1 : e;
+    }
+    return count > 0;
+}
+
+// Pinned host memory, placed on the NUMA node of the current device: the pages are allocated (first touched) inside
+// cudaMallocHost by the calling thread, so the thread is moved onto the device's local CPUs for the duration of the call.
+// Matters on multi-socket hosts, where a buffer on the far socket sends every PCIe transfer of the host pipeline
+// (fftb200_plan_exec_host) across the inter-socket link; the boxes measured so far expose one NUMA node (no effect there:
+// 2 GPUs, 121.6 ms per e2e step either way). FFTB200_NO_NUMA (set to anything) switches the placement off.
 extern "C" void* fftb200_host_alloc(size_t bytes) {
     void* p = nullptr;
     if (bytes == 0) bytes = 16;
+    cpu_set_t old_set, dev_set;
+    bool moved = false;
+    if (!getenv("FFTB200_NO_NUMA") && sched_getaffinity(0, sizeof(old_set), &old_set) == 0 && device_local_cpus(&dev_set)) {
+        cpu_set_t both;
+        CPU_AND(&both, &old_set, &dev_set);             // stay inside what the process is allowed to use
+        if (CPU_COUNT(&both) > 0 && !CPU_EQUAL(&both, &old_set)) moved = sched_setaffinity(0, sizeof(both), &both) == 0;
+    }
     cudaError_t e = cudaMallocHost(&p, bytes);
+    if (moved) sched_setaffinity(0, sizeof(old_set), &old_set);
     if (e != cudaSuccess) { fail("cudaMallocHost(%zu): %s", bytes, cudaGetErrorString(e)); cudaGetLastError(); return nullptr; }
     return p;
 }
