@@ -1,6 +1,7 @@
 // Persistent TMA-fed whole-transform kernels, N = 512 .. 4096 (fft_pipe.cuh).
 #include "fft_catalog.h"
 #include "fft_pipe.cuh"
+#include "fft_pipe13.cuh"
 namespace fftb200 {
 
 template <int LOGN, bool INV>
@@ -25,5 +26,15 @@ void launch_pipe(int logn, const PipeArgs& a, int grid, cudaStream_t s) {
         PIPE_CASES(X)
 #undef X
     }
+}
+
+// N = 8192: two 4096-point halves per transform, de-interleaved by the TMA (fft_pipe13.cuh)
+const void* pipe13_func(int inverse) {
+    return inverse ? (const void*)fft_pipe13_kernel<true> : (const void*)fft_pipe13_kernel<false>;
+}
+cudaError_t launch_pipe13(const PipeArgs& a, const CUtensorMap& tm, int grid, cudaStream_t s) {
+    if (a.inverse) fft_pipe13_kernel<true><<<grid, 2 * PIPE_GROUP, PIPE13_SMEM, s>>>(a, tm);
+    else fft_pipe13_kernel<false><<<grid, 2 * PIPE_GROUP, PIPE13_SMEM, s>>>(a, tm);
+    return cudaGetLastError();
 }
 }  // namespace fftb200

@@ -1,0 +1,234 @@
+// fft_pipe13.cuh - whole transforms of 8192 points in ONE visit to shared memory (HBM sees the algorithmic 32 bytes
+// per point and nothing passes through L2 twice): the 2^13 member of the fft_pipe.cuh family.
+//
+// Replaces the same reference code as fft_pipe.cuh (the butterfly loop of algorithms/core/radix2_dit.c:70-119 and the
+// never-built cufftExecZ2Z call of gpu/fft_cuda.cu:166-185) for N = 8192, where one transform is two 64 KB tiles.
+//
+// Decomposition N = 4096 * 2 in the reference's DIT order: stages 1 .. 12 are two independent 4096-point transforms
+// of the even and the odd samples x[c + 2 t] (c = 0, 1), stage 13 combines X[k], X[k + 4096] = Y0[k] +- w^k Y1[k].
+//   * the de-interleave is done by the TMA: the input is described as a [transform][t][c][re, im] tensor and a "half"
+//     (one c of one transform, 64 KB) arrives as 16 boxes of 256 rows of 16 bytes. Strided 16-byte rows cost the TMA
+//     one row per clock (tools/clbench.cu: 4.0 TB/s chip-wide), which is above what the HBM roofline asks for reads
+//     (3.3 TB/s), and the LSU - the most loaded pipe of fft_pipe_kernel - sees none of it;
+//   * group c (256 threads) runs the unchanged 4096-point dataflow of fft_pipe_kernel<12> on half c: the halves
+//     h = 2 k + c of this CTA's transforms k go through the same three-buffer ring with the same two-barriers-per-
+//     buffer scheme (tile index = h);
+//   * stage 13: each thread holds Y_c[t + 256 q], q < 16. Group 0 does the butterflies q < 8, group 1 q >= 8: the
+//     halves trade 8 values per thread through group 1's buffer (32 KB each way), and since
+//     w13[k + 2048] = -i w13[k] both groups use w13[t + 256 e] = w13[t] * W32^e (one table entry per thread, kept in
+//     registers). Group 0's buffer is not involved, so it is refilled as early as in fft_pipe_kernel (after the last
+//     gather): that load - the odd half of the NEXT transform - is the one on the critical path, the even half of
+//     the transform after it goes into group 1's buffer after the trade;
+//   * results leave from registers, X[k] and X[k + 4096], 512 contiguous bytes per warp instruction.
+// Twiddles are the accurate tables for all 13 stages (SURVEY.md 7.0 hybrid rule; 8192-point mismatch vs the
+// reference recurrence ~4e-14, checked by the GPU parity tests at 1e-12).
+#pragma once
+#include "fft_fused.cuh"
+
+namespace fftb200 {
+
+__device__ __forceinline__ void bar_sync_n(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+__device__ __forceinline__ void bar_arrive_n(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+
+// exp(-2 pi i e / 32), e < 8
+template <int E> struct W32 {
+    static constexpr double c = E == 0 ? 1.0 : E == 1 ? 0.98078528040323044913 : E == 2 ? 0.92387953251128675613 : E == 3 ? 0.83146961230254523708
+                              : E == 4 ? 0.70710678118654752440 : E == 5 ? 0.55557023301960222474 : E == 6 ? 0.38268343236508977173 : 0.19509032201612826785;
+    static constexpr double s = W32<8 - E>::c;
+};
+template <> struct W32<8> { static constexpr double c = 0.0, s = 1.0; };
+
+// stage 13 for the 8 positions k = k0 + 256 e of one thread: w13[t + 256 e] = w13[t] * W32^e; the upper half of the
+// positions (group 1, MI) uses -i times that. own[e] is this group's Y, z[e] the other group's.
+template <bool INV, bool MI, int E>
+struct Stage13 {
+    static __device__ __forceinline__ void run(const cd* own, const cd* z, const cd w13, cd* p, const double sc) {
+        const cd w = E == 0 ? w13 : cmulc(w13, W32<E>::c, -W32<E>::s);
+        cd lo, hi;
+        if constexpr (!MI) { lo = own[E]; hi = z[E]; bfly(lo, hi, w); }
+        else { lo = z[E]; hi = own[E]; bfly_mi(lo, hi, w); }
+        if (INV) { lo.x *= sc; lo.y *= -sc; hi.x *= sc; hi.y *= -sc; }
+        p[256 * E] = lo;
+        p[256 * E + 4096] = hi;
+        if constexpr (E < 7) Stage13<INV, MI, E + 1>::run(own, z, w13, p, sc);
+    }
+};
+
+#ifndef PIPE13_V
+#define PIPE13_V 1
+#endif
+constexpr size_t PIPE13_SMEM = PIPE_SMEM + 2048 * sizeof(cd);
+
+template <bool INV>
+__global__ void __launch_bounds__(2 * PIPE_GROUP, 1) fft_pipe13_kernel(const PipeArgs a, const __grid_constant__ CUtensorMap tm_in) {
+    constexpr int N = 8192, H = 4096;
+    constexpr int LN16 = 8;
+
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    cd* const bufs = reinterpret_cast<cd*>(smem_raw);
+    cd* const tw1s = bufs + (size_t)PIPE_STAGES * PIPE_TILE;
+    uint64_t* const full = reinterpret_cast<uint64_t*>(tw1s + PIPE_TW1);
+    cd* const trade = reinterpret_cast<cd*>(smem_raw + PIPE_SMEM);   // 32 KB: group 0's half of the stage-13 trade
+
+    const int g = threadIdx.x / PIPE_GROUP, t = threadIdx.x % PIPE_GROUP;
+    const int first = blockIdx.x, stride = gridDim.x;
+    const int my_tr = first < a.ntiles ? (int)((a.ntiles - first + stride - 1) / stride) : 0;   // transforms of this CTA
+    const int my_halves = 2 * my_tr;
+
+    // half h = 2 k + c of this CTA's k-th transform -> buffer b (= h % 3), 16 boxes of 256 rows x 16 bytes
+    auto issue = [&](int h, int b, uint32_t rnd) {
+        const long long tr = first + (long long)(h >> 1) * stride;
+        uint64_t* const bar = &full[b + PIPE_STAGES * (rnd & 1)];
+        mbar_expect_tx(bar, H * (uint32_t)sizeof(cd));
+        cd* dst = bufs + (size_t)b * PIPE_TILE;
+        uint64_t pol;
+        asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(pol));
+#pragma unroll 1
+        for (int i = 0; i < 16; i++) tma_load_4d(dst + 256 * i, &tm_in, 0, h & 1, 256 * i, (int)tr, bar, pol);
+    };
+
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int b = 0; b < 2 * PIPE_STAGES; b++) mbar_init(&full[b], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    // middle sub-pass twiddles -> shared: stage (4 + s), position kloc (fft_pipe.cuh)
+    if (threadIdx.x < 16 * 8) {
+        const int kl = threadIdx.x >> 3, e = threadIdx.x & 7;
+        tw1s[threadIdx.x] = __ldg(a.tab + ((sym_h(e) << 4) + kl - 1));
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int h = 0; h < PIPE_STAGES && h < my_halves; h++) issue(h, h, 0);
+    }
+
+    const int cp = t & 15, kloc1 = t >> 4;
+    const cd wa = __ldg(a.tab + (t - 1) + (1 << LN16)), wb = __ldg(a.tab + (t - 1) + (2 << LN16));
+    const cd wc = __ldg(a.tab + (t - 1) + (4 << LN16)), wd = __ldg(a.tab + (t - 1) + (8 << LN16));
+    const int rd1 = cp + 256 * kloc1;
+    const cd* const tw1p = tw1s + kloc1 * 8;
+    const double sc = a.scale;
+
+    int b = g;                 // ring slot of half h (h % 3)
+    uint32_t round = 0;        // h / 3
+    for (int h = g; h < my_halves; h += 2) {
+        cd* const sm = bufs + (size_t)b * PIPE_TILE;
+        mbar_wait(&full[b + PIPE_STAGES * (round & 1)], (round >> 1) & 1);
+        cd x[16];
+        // ---- sub-pass 0: radix 16, exact constants, in place ----
+#pragma unroll
+        for (int e = 0; e < 16; e++) {
+            cd y = sm[t + 256 * e];
+            if (INV) y.y = -y.y;
+            x[bitrev_c<4>(e)] = y;
+        }
+        SubStageExact<4, 1, 0, 0>::run(x);
+        __syncwarp();
+#pragma unroll
+        for (int e = 0; e < 16; e++) sm[pipe_swz(t + 256 * e)] = x[e];
+        group_sync(g);
+        // ---- sub-pass 1: radix 16 after 4 stages ----
+        {
+            cd y[16];
+#pragma unroll
+            for (int rho = 0; rho < 16; rho++) y[bitrev_c<4>(rho)] = sm[pipe_swz(rd1 + 16 * rho)];
+            cd tw[16];
+            load_sym(tw, tw1p);
+            SubStageSym<4, 1, 0, 0>::run(y, tw);
+            group_sync(g);
+#pragma unroll
+            for (int q = 0; q < 16; q++) sm[pipe_swz(t + (q << LN16))] = y[q];
+        }
+        group_sync(g);
+        // ---- sub-pass 2: radix 16 after 8 stages ----
+#pragma unroll
+        for (int rho = 0; rho < 16; rho++) x[bitrev_c<4>(rho)] = sm[pipe_swz(16 * t + rho)];
+        group_sync(g);
+        // group 0's buffer is free now: refill it with half h + 3 (the odd half of the next transform)
+        if (g == 0 && t == 0 && h + PIPE_STAGES < my_halves) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            issue(h + PIPE_STAGES, b, round + 1);
+        }
+#if PIPE13_V == 1
+        if (g == 1) bar_arrive_n(3, 2 * PIPE_GROUP);
+#endif
+        {
+            constexpr double C8 = 0.70710678118654752440, C16 = 0.92387953251128675613, S16 = 0.38268343236508977173;
+            cd tw[16];
+            tw[1] = wa; tw[2] = wb; tw[4] = wc; tw[8] = wd;
+            tw[5] = make_double2((wc.x + wc.y) * C8, (wc.y - wc.x) * C8);
+            tw[9] = cmulc(wd, C16, -S16);
+            tw[10] = make_double2((wd.x + wd.y) * C8, (wd.y - wd.x) * C8);
+            tw[11] = cmulc(wd, S16, -C16);
+            SubStageSym<4, 1, 0, 0>::run(x, tw);
+        }
+        // ---- stage 13: x[q] = Y_g[t + 256 q]. Group 0 leaves its q >= 8 in the trade area, group 1 its q < 8 in the lower
+        //      half of its own buffer (all of its gathers are done). One CTA-wide rendezvous per transform (barrier 4); the
+        //      other two barriers only order buffer reuse and are normally satisfied long before they are looked at:
+        //      3 = group 1 has read the trade area (group 0 waits before writing it again), 5 = group 0 has read group 1's
+        //      buffer (group 1's first warp waits, then refills it with half h + 3). ----
+        cd z[8];
+#if PIPE13_V == 1
+        // variant 1: both halves of the trade go through group 1's buffer; three CTA-wide barriers per transform
+        {
+            cd* const xb = bufs + (size_t)(g == 0 ? (b + 1 == PIPE_STAGES ? 0 : b + 1) : b) * PIPE_TILE;   // buffer of half 2k + 1
+            if (g == 0) {
+                bar_sync_n(3, 2 * PIPE_GROUP);   // group 1 has gathered its last sub-pass
+#pragma unroll
+                for (int e = 0; e < 8; e++) xb[256 * e + t] = x[8 + e];
+            } else {
+#pragma unroll
+                for (int e = 0; e < 8; e++) xb[2048 + 256 * e + t] = x[e];
+            }
+            bar_sync_n(4, 2 * PIPE_GROUP);
+#pragma unroll
+            for (int e = 0; e < 8; e++) z[e] = xb[(g == 0 ? 2048 : 0) + 256 * e + t];
+            bar_sync_n(5, 2 * PIPE_GROUP);       // the trade has been read: group 1's buffer is free
+            if (g == 1 && t == 0 && h + PIPE_STAGES < my_halves) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                issue(h + PIPE_STAGES, b, round + 1);
+            }
+        }
+#else
+        if (g == 0) {
+            if (h > 0) bar_sync_n(3, 2 * PIPE_GROUP);
+#pragma unroll
+            for (int e = 0; e < 8; e++) trade[256 * e + t] = x[8 + e];
+            bar_sync_n(4, 2 * PIPE_GROUP);
+            const cd* const xb = bufs + (size_t)(b + 1 == PIPE_STAGES ? 0 : b + 1) * PIPE_TILE;   // buffer of half h + 1
+#pragma unroll
+            for (int e = 0; e < 8; e++) z[e] = xb[256 * e + t];
+            bar_arrive_n(5, PIPE_GROUP + 32);
+        } else {
+#pragma unroll
+            for (int e = 0; e < 8; e++) sm[256 * e + t] = x[e];
+            bar_sync_n(4, 2 * PIPE_GROUP);
+#pragma unroll
+            for (int e = 0; e < 8; e++) z[e] = trade[256 * e + t];
+            if (h + 2 < my_halves) bar_arrive_n(3, 2 * PIPE_GROUP);
+            if (t < 32) {
+                bar_sync_n(5, PIPE_GROUP + 32);
+                if (t == 0 && h + PIPE_STAGES < my_halves) {
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    issue(h + PIPE_STAGES, b, round + 1);
+                }
+            }
+        }
+#endif
+        {
+            const long long tr = first + (long long)(h >> 1) * stride;
+            cd* const p = a.out + tr * N + t + (g ? 2048 : 0);
+            const cd w13 = __ldg(a.tab + (H - 1) + t);   // stage 13, position t (L1-resident: the same entry for every transform)
+            if (g == 0) Stage13<INV, false, 0>::run(x, z, w13, p, sc);
+            else Stage13<INV, true, 0>::run(x + 8, z, w13, p, sc);
+        }
+        b += 2;
+        if (b >= PIPE_STAGES) { b -= PIPE_STAGES; round++; }
+    }
+}
+
+const void* pipe13_func(int inverse);
+cudaError_t launch_pipe13(const PipeArgs& a, const CUtensorMap& tm, int grid, cudaStream_t s);
+
+}  // namespace fftb200

@@ -308,9 +308,11 @@ __global__ void __launch_bounds__(C::THREADS, C::MINB) fft_tile_kernel(const Til
             cx.out_rs = 1LL << (log_rest + log_m);
             cx.kap_base = (int)k; cx.kap_col = 0;
         } else {
-            const int log_tpx = log_m - C::LOGC;                    // tiles per transform = M / C
-            const long long b = tile >> log_tpx;
-            const long long k0 = (tile & ((1LL << log_tpx) - 1)) << C::LOGC;
+            // transform index fastest: the batch walks through the same k block back to back, so the block's late-stage
+            // twiddles (as many bytes as the tile itself, every table entry used once per transform) come from L2 for all
+            // but the first transform. 2^24 x 16: DRAM reads 8.63 -> 4.6 GB per execution.
+            const long long b = tile % a.batch;
+            const long long k0 = (tile / a.batch) << C::LOGC;
             cx.valid = true;
             cx.in_base = (b << log_n) + (k0 << C::LOGP);
             cx.in_rs = 0;

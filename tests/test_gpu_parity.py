@@ -235,7 +235,7 @@ def test_config2_full_size_round_trip_and_samples(gpu, port, O):
 
 @pytest.mark.parametrize("log_n,batch", [(13, 5000), (14, 3001), (15, 777), (16, 1000), (17, 300), (18, 100), (19, 37), (20, 24)])
 def test_fused_two_pass_many_groups(gpu, port, O, log_n, batch):
-    """N = 2^13 .. 2^20 run in the fused two-pass kernel (csrc/fft_fused.cuh). Batches large enough that the
+    """N = 2^14 .. 2^20 (and 2^13 under FFTB200_NO_PIPE13) run in the fused two-pass kernel (csrc/fft_fused.cuh). Batches large enough that the
     L2-resident scratch ring wraps many times and ragged against its grouping: sampled transforms against the
     oracle, Parseval over the whole job, then the in-place inverse of everything against the input."""
     import torch
@@ -263,6 +263,53 @@ def test_fused_two_pass_many_groups(gpu, port, O, log_n, batch):
     assert err <= (TOL if log_n <= 16 else 2e-11)  # the reference's own round trip is 1e-11 at 2^20 (twiddle recurrence)
     L.fft_gpu_destroy_plan(fwd)
     L.fft_gpu_destroy_plan(inv)
+
+
+@pytest.mark.parametrize("batch", [1, 2, 3, 147, 149, 445, 5000])
+def test_pipe13_one_visit_kernel(gpu, port, O, batch):
+    """N = 8192 runs in fft_pipe13_kernel (csrc/fft_pipe13.cuh): two TMA-de-interleaved 4096-point halves per transform in
+    a three-buffer ring, stage 13 traded between the two thread groups. Batches below, at and ragged against the grid
+    (148 CTAs), so CTAs with 0, 1, 2 and many transforms and every ring phase are exercised; forward against the oracle,
+    the same plan twice, then the in-place inverse of everything against the input."""
+    import torch
+    L = gpu.lib
+    n = 1 << 13
+    x = torch.empty((batch, n), dtype=torch.complex128, device="cuda")
+    y = torch.empty_like(x)
+    assert L.fftb200_fill_splitmix(x.data_ptr(), 50, 0, n * batch) == 0
+    torch.cuda.synchronize()
+    fwd = L.fft_gpu_plan_1d(n, batch, -1)
+    inv = L.fft_gpu_plan_1d(n, batch, 1)
+    assert fwd and inv
+    assert b"P13" in L.fftb200_plan_describe(L.fftb200_engine_of(fwd))
+    for _ in range(2):
+        assert L.fftb200_plan_exec(L.fftb200_engine_of(fwd), x.data_ptr(), y.data_ptr()) == 0
+    rng = np.random.default_rng(batch)
+    rows = np.unique(np.concatenate([[0, batch - 1], rng.integers(0, batch, 8)]))
+    got = y[torch.as_tensor(rows, device="cuda")].cpu().numpy()
+    xin = np.stack([port.fill(50, int(r) * n, n) for r in rows])
+    assert O.rel_l2(got, port.fft_batch(xin, -1)) <= TOL
+    ex, ey = float((x.real ** 2 + x.imag ** 2).sum()), float((y.real ** 2 + y.imag ** 2).sum())
+    assert abs(ey / (n * ex) - 1) <= 1e-12
+    assert L.fftb200_plan_exec(L.fftb200_engine_of(inv), y.data_ptr(), y.data_ptr()) == 0  # in place
+    err = float(torch.linalg.vector_norm(y - x) / torch.linalg.vector_norm(x))
+    assert err <= TOL
+    L.fft_gpu_destroy_plan(fwd)
+    L.fft_gpu_destroy_plan(inv)
+
+
+def test_fused_kernel_at_2_13_agrees_with_pipe13(gpu, port, O, monkeypatch):
+    """FFTB200_NO_PIPE13=1 plans N = 8192 in the fused two-pass kernel (Z7+6) as before; both routes must match the oracle
+    and each other to the parity bar (they differ only in the stage-8 .. 13 twiddle tables: reference recurrence vs accurate)."""
+    n, batch = 1 << 13, 333
+    x = port.fill(51, 0, n * batch).reshape(batch, n)
+    a = gpu.gpu_fft_batch(x, -1)
+    monkeypatch.setenv("FFTB200_NO_PIPE13", "1")
+    b = gpu.gpu_fft_batch(x, -1)
+    monkeypatch.delenv("FFTB200_NO_PIPE13")
+    want = port.fft_batch(x[:4], -1)
+    assert O.rel_l2(a[:4], want) <= TOL and O.rel_l2(b[:4], want) <= TOL
+    assert O.rel_l2(a, b) <= 1e-13
 
 
 def test_two_fused_plans_run_concurrently(gpu, port, O):
