@@ -33,8 +33,8 @@ const void* pipe13_func(int inverse) {
     return inverse ? (const void*)fft_pipe13_kernel<true> : (const void*)fft_pipe13_kernel<false>;
 }
 cudaError_t launch_pipe13(const PipeArgs& a, const CUtensorMap& tm, int grid, cudaStream_t s) {
-    if (a.inverse) fft_pipe13_kernel<true><<<grid, 2 * PIPE_GROUP, PIPE13_SMEM, s>>>(a, tm);
-    else fft_pipe13_kernel<false><<<grid, 2 * PIPE_GROUP, PIPE13_SMEM, s>>>(a, tm);
+    if (a.inverse) fft_pipe13_kernel<true><<<grid, 2 * PIPE_GROUP, PIPE_SMEM, s>>>(a, tm);
+    else fft_pipe13_kernel<false><<<grid, 2 * PIPE_GROUP, PIPE_SMEM, s>>>(a, tm);
     return cudaGetLastError();
 }
 }  // namespace fftb200

@@ -15,13 +15,13 @@
 //     buffer scheme (tile index = h);
 //   * stage 13: each thread holds Y_c[t + 256 q], q < 16. Group 0 does the butterflies q < 8, group 1 q >= 8: the
 //     halves trade 8 values per thread through group 1's buffer (32 KB each way), and since
-//     w13[k + 2048] = -i w13[k] both groups use w13[t + 256 e] = w13[t] * W32^e (one table entry per thread, kept in
-//     registers). Group 0's buffer is not involved, so it is refilled as early as in fft_pipe_kernel (after the last
-//     gather): that load - the odd half of the NEXT transform - is the one on the critical path, the even half of
+//     w13[k + 2048] = -i w13[k] both groups use w13[t + 256 e] = w13[t] * W32^e (one table entry per thread, re-read from
+//     L1 per transform to keep the register file free of spills). Group 0's buffer is not involved, so it is refilled
+//     as early as in fft_pipe_kernel (after the last gather): that load - the odd half of the NEXT transform - is the one on the critical path, the even half of
 //     the transform after it goes into group 1's buffer after the trade;
 //   * results leave from registers, X[k] and X[k + 4096], 512 contiguous bytes per warp instruction.
 // Twiddles are the accurate tables for all 13 stages (SURVEY.md 7.0 hybrid rule; 8192-point mismatch vs the
-// reference recurrence ~4e-14, checked by the GPU parity tests at 1e-12).
+// reference recurrence 2.6e-14, checked by the GPU parity tests at 1e-12).
 #pragma once
 #include "fft_fused.cuh"
 
@@ -54,11 +54,6 @@ struct Stage13 {
     }
 };
 
-#ifndef PIPE13_V
-#define PIPE13_V 1
-#endif
-constexpr size_t PIPE13_SMEM = PIPE_SMEM + 2048 * sizeof(cd);
-
 template <bool INV>
 __global__ void __launch_bounds__(2 * PIPE_GROUP, 1) fft_pipe13_kernel(const PipeArgs a, const __grid_constant__ CUtensorMap tm_in) {
     constexpr int N = 8192, H = 4096;
@@ -68,7 +63,6 @@ __global__ void __launch_bounds__(2 * PIPE_GROUP, 1) fft_pipe13_kernel(const Pip
     cd* const bufs = reinterpret_cast<cd*>(smem_raw);
     cd* const tw1s = bufs + (size_t)PIPE_STAGES * PIPE_TILE;
     uint64_t* const full = reinterpret_cast<uint64_t*>(tw1s + PIPE_TW1);
-    cd* const trade = reinterpret_cast<cd*>(smem_raw + PIPE_SMEM);   // 32 KB: group 0's half of the stage-13 trade
 
     const int g = threadIdx.x / PIPE_GROUP, t = threadIdx.x % PIPE_GROUP;
     const int first = blockIdx.x, stride = gridDim.x;
@@ -145,14 +139,16 @@ __global__ void __launch_bounds__(2 * PIPE_GROUP, 1) fft_pipe13_kernel(const Pip
 #pragma unroll
         for (int rho = 0; rho < 16; rho++) x[bitrev_c<4>(rho)] = sm[pipe_swz(16 * t + rho)];
         group_sync(g);
-        // group 0's buffer is free now: refill it with half h + 3 (the odd half of the next transform)
-        if (g == 0 && t == 0 && h + PIPE_STAGES < my_halves) {
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            issue(h + PIPE_STAGES, b, round + 1);
+        // group 0's buffer is free now: refill it with half h + 3 (the odd half of the next transform). Group 1's buffer
+        // hosts the stage-13 trade first: tell group 0 that every gather from it is done.
+        if (g == 0) {
+            if (t == 0 && h + PIPE_STAGES < my_halves) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                issue(h + PIPE_STAGES, b, round + 1);
+            }
+        } else {
+            bar_arrive_n(3, 2 * PIPE_GROUP);
         }
-#if PIPE13_V == 1
-        if (g == 1) bar_arrive_n(3, 2 * PIPE_GROUP);
-#endif
         {
             constexpr double C8 = 0.70710678118654752440, C16 = 0.92387953251128675613, S16 = 0.38268343236508977173;
             cd tw[16];
@@ -163,14 +159,12 @@ __global__ void __launch_bounds__(2 * PIPE_GROUP, 1) fft_pipe13_kernel(const Pip
             tw[11] = cmulc(wd, S16, -C16);
             SubStageSym<4, 1, 0, 0>::run(x, tw);
         }
-        // ---- stage 13: x[q] = Y_g[t + 256 q]. Group 0 leaves its q >= 8 in the trade area, group 1 its q < 8 in the lower
-        //      half of its own buffer (all of its gathers are done). One CTA-wide rendezvous per transform (barrier 4); the
-        //      other two barriers only order buffer reuse and are normally satisfied long before they are looked at:
-        //      3 = group 1 has read the trade area (group 0 waits before writing it again), 5 = group 0 has read group 1's
-        //      buffer (group 1's first warp waits, then refills it with half h + 3). ----
+        // ---- stage 13: x[q] = Y_g[t + 256 q]. Trade through group 1's buffer: group 0 leaves its q >= 8 in the lower
+        //      32 KB, group 1 its q < 8 in the upper 32 KB. Measured alternatives (same box, ms at 2^28 points): this form
+        //      2.05; group 0's half in a separate 32 KB area and only the refilling warp waiting for the reads (one
+        //      blocking CTA-wide barrier instead of three) 2.13; barrier 5 waited for by the refilling warp alone 2.06;
+        //      group 1 held back by 200 / 400 / 800 ns per transform to take the groups out of phase 2.17 / 2.17 / 2.19 ----
         cd z[8];
-#if PIPE13_V == 1
-        // variant 1: both halves of the trade go through group 1's buffer; three CTA-wide barriers per transform
         {
             cd* const xb = bufs + (size_t)(g == 0 ? (b + 1 == PIPE_STAGES ? 0 : b + 1) : b) * PIPE_TILE;   // buffer of half 2k + 1
             if (g == 0) {
@@ -190,32 +184,6 @@ __global__ void __launch_bounds__(2 * PIPE_GROUP, 1) fft_pipe13_kernel(const Pip
                 issue(h + PIPE_STAGES, b, round + 1);
             }
         }
-#else
-        if (g == 0) {
-            if (h > 0) bar_sync_n(3, 2 * PIPE_GROUP);
-#pragma unroll
-            for (int e = 0; e < 8; e++) trade[256 * e + t] = x[8 + e];
-            bar_sync_n(4, 2 * PIPE_GROUP);
-            const cd* const xb = bufs + (size_t)(b + 1 == PIPE_STAGES ? 0 : b + 1) * PIPE_TILE;   // buffer of half h + 1
-#pragma unroll
-            for (int e = 0; e < 8; e++) z[e] = xb[256 * e + t];
-            bar_arrive_n(5, PIPE_GROUP + 32);
-        } else {
-#pragma unroll
-            for (int e = 0; e < 8; e++) sm[256 * e + t] = x[e];
-            bar_sync_n(4, 2 * PIPE_GROUP);
-#pragma unroll
-            for (int e = 0; e < 8; e++) z[e] = trade[256 * e + t];
-            if (h + 2 < my_halves) bar_arrive_n(3, 2 * PIPE_GROUP);
-            if (t < 32) {
-                bar_sync_n(5, PIPE_GROUP + 32);
-                if (t == 0 && h + PIPE_STAGES < my_halves) {
-                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                    issue(h + PIPE_STAGES, b, round + 1);
-                }
-            }
-        }
-#endif
         {
             const long long tr = first + (long long)(h >> 1) * stride;
             cd* const p = a.out + tr * N + t + (g ? 2048 : 0);

@@ -331,7 +331,7 @@ static int build_passes(fftb200_plan* p, DeviceState* ds) {
         ps.nt = 1; ps.shift = 0;
         ps.src = BUF_IN; ps.dst = BUF_OUT; ps.final_pass = 1;
         for (int iv = 0; iv < 2; iv++)
-            CU(cudaFuncSetAttribute(pipe13_func(iv), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PIPE13_SMEM));
+            CU(cudaFuncSetAttribute(pipe13_func(iv), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PIPE_SMEM));
         ps.grid_max = ds->sms;
         p->passes.push_back(ps);
         p->desc += "P13(tma de-interleave, ring 3 x 64KB halves, 2x256 thr, stage 13 traded through shared memory)";
