@@ -45,7 +45,17 @@ struct TileArgs {
     // ((row & (2^peer_lrows - 1)) << (peer_lw + peer_lg)) + (peer_me << peer_lw) + col. peers == nullptr: local.
     cd* const* peers;
     int peer_lw, peer_lrows, peer_lg, peer_me;
+    // Bluestein (bluestein.c:107-148): the chirp multiplications and the spectral product ride on the first / last pass
+    // instead of running as elementwise kernels of their own (three HBM round trips less per transform).
+    //   MUL_PRE   first pass: reads the caller's x (n per transform), element idx < n is x[idx] * conj(mul[idx]), the rest 0
+    //   MUL_FB    last pass of the forward transform: X[idx] * mul[idx] (mul = FFT of the wrapped chirp, m entries)
+    //   MUL_POST  last pass of the inverse transform: y[idx] = a[idx] * conj(mul[idx]) * mul_scale for idx < n, stored to
+    //             the caller's y (n per transform)
+    const cd* mul;
+    int mul_mode, mul_n;
+    double mul_scale;
 };
+enum { MUL_NONE = 0, MUL_PRE = 1, MUL_FB = 2, MUL_POST = 3 };
 
 __device__ __forceinline__ cd* peer_ptr(const TileArgs& a, long long idx) {
     const long long row = idx >> a.peer_lw, col = idx & ((1LL << a.peer_lw) - 1);
@@ -161,6 +171,7 @@ template <class C> __device__ __forceinline__ int smpos(int idx) { return idx + 
 
 struct TileCtx {
     long long in_base, out_base, in_rs, out_rs;  // element offsets / row strides
+    long long tb;                                // transform index (fused Bluestein factors address per transform)
     int kap_base, kap_col;
     bool valid;
 };
@@ -210,12 +221,28 @@ __device__ __forceinline__ void subpass(cd (&v)[C::E], cd* __restrict__ sm, cons
                 // f = u + rho * NP/R ; (row, col) = (f >> LOGC, f & CM) ; col is fixed per thread
                 const cd* p = a.in + cx.in_base + (u & CM) + (long long)(u >> C::LOGC) * cx.in_rs;
                 const long long step = (long long)(C::NP >> (LR + C::LOGC)) * cx.in_rs;
+                if (C::MODE == MODE_STRIDED && a.mul_mode == MUL_PRE) {
+                    // a = x * conj(chirp), zero-padded from n to m (bluestein.c:107-109)
+                    const long long i0 = cx.in_base - (cx.tb << a.log_n) + (u & CM) + (long long)(u >> C::LOGC) * cx.in_rs;
+                    const cd* xin = a.in + cx.tb * a.mul_n;
 #pragma unroll
-                for (int rho = 0; rho < R; rho++) {
-                    cd x = make_double2(0.0, 0.0);
-                    if (cx.valid) x = p[rho * step];
-                    if (a.inverse) x.y = -x.y;
-                    v[b * R + bitrev_c<LR>(rho)] = x;
+                    for (int rho = 0; rho < R; rho++) {
+                        const long long idx = i0 + rho * step;
+                        cd x = make_double2(0.0, 0.0);
+                        if (idx < a.mul_n) {
+                            const cd xv = xin[idx], w = __ldg(a.mul + idx);
+                            x = make_double2(fma(xv.x, w.x, xv.y * w.y), fma(xv.y, w.x, -(xv.x * w.y)));
+                        }
+                        v[b * R + bitrev_c<LR>(rho)] = x;
+                    }
+                } else {
+#pragma unroll
+                    for (int rho = 0; rho < R; rho++) {
+                        cd x = make_double2(0.0, 0.0);
+                        if (cx.valid) x = p[rho * step];
+                        if (a.inverse) x.y = -x.y;
+                        v[b * R + bitrev_c<LR>(rho)] = x;
+                    }
                 }
             }
         } else {
@@ -254,6 +281,33 @@ __device__ __forceinline__ void subpass(cd (&v)[C::E], cd* __restrict__ sm, cons
             const long long o = cx.out_base + (u & CM) + (long long)(u >> C::LOGC) * cx.out_rs;
             cd* p = a.out + o;
             const long long step = (long long)(C::NP >> (LR + C::LOGC)) * cx.out_rs;
+            if (C::MODE == MODE_LAST && a.mul_mode != MUL_NONE) {
+                // factors are fetched four at a time ahead of the stores they feed (a load cannot be hoisted over a store
+                // by the compiler: the pointers may alias)
+                const long long i0 = o - (cx.tb << a.log_n);   // index within the transform
+                const bool fb = a.mul_mode == MUL_FB;
+                const long long lim = fb ? (1LL << a.log_n) : a.mul_n;
+                const double s2 = a.mul_scale;
+                cd* const yo = a.out + cx.tb * a.mul_n;
+#pragma unroll
+                for (int q0 = 0; q0 < R; q0 += 4) {
+                    cd w[4];
+#pragma unroll
+                    for (int j = 0; j < 4 && q0 + j < R; j++) {
+                        const long long idx = i0 + (q0 + j) * step;
+                        w[j] = idx < lim ? __ldg(a.mul + idx) : make_double2(0.0, 0.0);
+                    }
+#pragma unroll
+                    for (int j = 0; j < 4 && q0 + j < R; j++) {
+                        cd x = v[b * R + q0 + j];
+                        if (conj_out) { x.x *= sc; x.y *= -sc; }
+                        const long long idx = i0 + (q0 + j) * step;
+                        if (fb) p[(q0 + j) * step] = make_double2(fma(x.x, w[j].x, -(x.y * w[j].y)), fma(x.x, w[j].y, x.y * w[j].x));
+                        else if (idx < lim) yo[idx] = make_double2(fma(x.x, w[j].x, x.y * w[j].y) * s2, fma(x.y, w[j].x, -(x.x * w[j].y)) * s2);
+                    }
+                }
+                continue;
+            }
 #pragma unroll
             for (int q = 0; q < R; q++) {
                 cd x = v[b * R + q];
@@ -289,6 +343,7 @@ __global__ void __launch_bounds__(C::THREADS, C::MINB) fft_tile_kernel(const Til
         if constexpr (C::MODE == MODE_CONTIG) {
             const long long b = tile * C::NT + st;
             cx.valid = b < a.batch;
+            cx.tb = b;
             cx.in_base = cx.out_base = b << log_n;
             cx.in_rs = cx.out_rs = 1;
             cx.kap_base = 0; cx.kap_col = 0;
@@ -302,6 +357,7 @@ __global__ void __launch_bounds__(C::THREADS, C::MINB) fft_tile_kernel(const Til
             const long long k = r >> log_tpk;
             const long long c0 = (r & ((1LL << log_tpk) - 1)) << C::LOGC;
             cx.valid = true;
+            cx.tb = b;
             cx.in_base = (b << log_n) + c0 + (k << (log_n - log_m));
             cx.in_rs = 1LL << log_rest;
             cx.out_base = (b << log_n) + c0 + (k << log_rest);
@@ -314,6 +370,7 @@ __global__ void __launch_bounds__(C::THREADS, C::MINB) fft_tile_kernel(const Til
             const long long b = tile % a.batch;
             const long long k0 = (tile / a.batch) << C::LOGC;
             cx.valid = true;
+            cx.tb = b;
             cx.in_base = (b << log_n) + (k0 << C::LOGP);
             cx.in_rs = 0;
             cx.out_base = (b << log_n) + k0;

@@ -75,6 +75,21 @@ def test_bluestein_parity(gpu, port, O, n, direction):
     assert O.rel_l2(y, want) <= TOL
 
 
+@pytest.mark.parametrize("direction", [-1, 1])
+def test_bluestein_fused_chirp_is_bit_identical(gpu, port, direction, monkeypatch):
+    """Multi-pass Bluestein plans (m >= 2^21) apply the chirp factors and the spectral product inside the first / last
+    tile pass (fft_tile.cuh MUL_*); FFTB200_NO_FUSED_CHIRP=1 runs them as separate elementwise kernels. Same arithmetic
+    in the same order: the outputs must be identical bit for bit (batch 3: ragged against the tile grid)."""
+    n, b = 1000003, 3
+    x = port.fill(52, 0, n * b).reshape(b, n)
+    fused = gpu.gpu_fft_batch(x, direction)
+    monkeypatch.setenv("FFTB200_NO_FUSED_CHIRP", "1")
+    plain = gpu.gpu_fft_batch(x, direction)
+    monkeypatch.delenv("FFTB200_NO_FUSED_CHIRP")
+    assert np.array_equal(fused, plain)
+    assert np.array_equal(gpu.gpu_fft_batch(x, direction, inplace=True), fused)
+
+
 @pytest.mark.parametrize("n", [2, 4, 64, 1024, 1 << 14, 1 << 17, 1 << 20])
 def test_r2c_parity(gpu, port, O, n):
     x = port.fill(47, 0, n).real.copy()

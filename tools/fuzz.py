@@ -43,7 +43,7 @@ while time.time() - t0 < budget:
             x = (rng.standard_normal((batch, n)) + 1j * rng.standard_normal((batch, n)))
             y = F.gpu_fft_batch(x, d)
             want = np.fft.fft(x, axis=1) if d < 0 else np.fft.ifft(x, axis=1)
-            e = rel(y, want); tag = ("blue", n, batch, d); lim = 1e-11
+            e = rel(y, want); tag = ("blue", n, batch, d); lim = 1e-10   # the reference recurrence at m = 2^17: ~2e-11
         elif kind == "r2c":
             n = 1 << int(rng.integers(1, 21))
             x = rng.standard_normal(n)

@@ -1,10 +1,12 @@
-"""Run one plan a few times (for ncu). usage: one.py log_n [batch] [reps] [direction]"""
+"""Run one plan a few times (for ncu). usage: one.py log_n|nN [batch] [reps] [direction]   (n1000003: that length, Bluestein)"""
 import os, sys
 sys.path.insert(0, os.path.join(os.path.dirname(__file__), ".."))
 import fftb200_loader
 F = fftb200_loader.load(); L = F.lib
 F.require_gpu()
-lg = int(sys.argv[1]); n = 1 << lg
+a1 = sys.argv[1]
+n = int(a1[1:]) if a1.startswith("n") else 1 << int(a1)
+lg = max(1, n.bit_length() - 1)
 batch = int(sys.argv[2]) if len(sys.argv) > 2 else (1 << 28) >> lg
 reps = int(sys.argv[3]) if len(sys.argv) > 3 else 3
 d = int(sys.argv[4]) if len(sys.argv) > 4 else -1
