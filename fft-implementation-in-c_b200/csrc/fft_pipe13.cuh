@@ -112,10 +112,10 @@ __global__ void __launch_bounds__(2 * PIPE_GROUP, 1) fft_pipe13_kernel(const Pip
         cd x[16];
         // ---- sub-pass 0: radix 16, exact constants, in place ----
 #pragma unroll
-        for (int e = 0; e < 16; e++) {
-            cd y = sm[t + 256 * e];
+        for (int i = 0; i < 16; i++) {   // in the order the butterflies consume them: the first pairs arrive first
+            cd y = sm[t + 256 * bitrev_c<4>(i)];
             if (INV) y.y = -y.y;
-            x[bitrev_c<4>(e)] = y;
+            x[i] = y;
         }
         SubStageExact<4, 1, 0, 0>::run(x);
         __syncwarp();
@@ -126,7 +126,7 @@ __global__ void __launch_bounds__(2 * PIPE_GROUP, 1) fft_pipe13_kernel(const Pip
         {
             cd y[16];
 #pragma unroll
-            for (int rho = 0; rho < 16; rho++) y[bitrev_c<4>(rho)] = sm[pipe_swz(rd1 + 16 * rho)];
+            for (int i = 0; i < 16; i++) y[i] = sm[pipe_swz(rd1 + 16 * bitrev_c<4>(i))];
             cd tw[16];
             load_sym(tw, tw1p);
             SubStageSym<4, 1, 0, 0>::run(y, tw);
@@ -137,7 +137,7 @@ __global__ void __launch_bounds__(2 * PIPE_GROUP, 1) fft_pipe13_kernel(const Pip
         group_sync(g);
         // ---- sub-pass 2: radix 16 after 8 stages ----
 #pragma unroll
-        for (int rho = 0; rho < 16; rho++) x[bitrev_c<4>(rho)] = sm[pipe_swz(16 * t + rho)];
+        for (int i = 0; i < 16; i++) x[i] = sm[pipe_swz(16 * t + bitrev_c<4>(i))];
         group_sync(g);
         // group 0's buffer is free now: refill it with half h + 3 (the odd half of the next transform). Group 1's buffer
         // hosts the stage-13 trade first: tell group 0 that every gather from it is done.
@@ -163,7 +163,9 @@ __global__ void __launch_bounds__(2 * PIPE_GROUP, 1) fft_pipe13_kernel(const Pip
         //      32 KB, group 1 its q < 8 in the upper 32 KB. Measured alternatives (same box, ms at 2^28 points): this form
         //      2.05; group 0's half in a separate 32 KB area and only the refilling warp waiting for the reads (one
         //      blocking CTA-wide barrier instead of three) 2.13; barrier 5 waited for by the refilling warp alone 2.06;
-        //      group 1 held back by 200 / 400 / 800 ns per transform to take the groups out of phase 2.17 / 2.17 / 2.19 ----
+        //      group 1 held back by 200 / 400 / 800 ns per transform to take the groups out of phase 2.17 / 2.17 / 2.19.
+        //      (Gathers issued in the order the butterflies consume them: 1.95 -> 1.90; the four last-sub-pass twiddles
+        //      re-read per transform instead of living in registers - no spills - 1.95.) ----
         cd z[8];
         {
             cd* const xb = bufs + (size_t)(g == 0 ? (b + 1 == PIPE_STAGES ? 0 : b + 1) : b) * PIPE_TILE;   // buffer of half 2k + 1
