@@ -265,6 +265,9 @@ struct fftb200_plan {
     cd* d_ring[NSTAGE] = {nullptr, nullptr, nullptr};   // chunked host pipeline: in-place staging buffers
     int ring_batch = 0;                                  // transforms per staging buffer
     cudaEvent_t ev_up[NSTAGE] = {}, ev_run[NSTAGE] = {}, ev_down[NSTAGE] = {};
+    char* h_zc = nullptr;      // small host transforms: page-locked staging the kernels read and write in place over PCIe (zero copy)
+    char* d_zc = nullptr;      // its device address
+    size_t zc_half = 0;        // bytes per direction
     cudaStream_t stream = nullptr, s_up = nullptr, s_down = nullptr;
     bool owns_stream = true;   // false after fftb200_plan_set_stream (plans chained on one stream, e.g. the two halves of a 2-D transform)
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -1052,6 +1055,34 @@ extern "C" int fftb200_plan_exec_host(fftb200_plan* p, const void* h_in, void* h
     // the fused r2c kernel cannot run in place: its staging buffers hold the real input followed by the half spectra
     const bool split = p->kind == FFTB200_R2C && !p->work;
     const size_t per = split ? in_per + out_per + 16 : (in_per > out_per ? in_per : out_per);
+    // Small single-kernel transforms (fft_auto on 1024 points: BASELINE config 1) are latency, not bandwidth: two cudaMemcpy
+    // calls and three streams cost ~40 us around a 9 us kernel. Instead the caller's data goes through a page-locked, device-
+    // mapped staging buffer of the plan and the kernel reads / writes it directly over PCIe: one launch, one synchronise.
+    {
+        const size_t in_bytes = in_per * (size_t)p->batch, out_bytes = out_per * (size_t)p->batch;
+        // (kernels that address global memory through tensor maps - N >= 8192 - keep the staged path)
+        const bool plain = p->passes.size() == 1 && !p->passes[0].fused_lm && p->passes[0].log_p <= 12;
+        const size_t big = in_bytes > out_bytes ? in_bytes : out_bytes;
+        if (plain && big <= (128u << 10) && !getenv("FFTB200_NO_ZEROCOPY")) {
+            if (!p->h_zc) {
+                const size_t half = (big + 255) & ~(size_t)255;
+                void* h = nullptr; void* d = nullptr;
+                if (cudaHostAlloc(&h, 2 * half, cudaHostAllocMapped) == cudaSuccess && cudaHostGetDevicePointer(&d, h, 0) == cudaSuccess) {
+                    p->h_zc = (char*)h; p->d_zc = (char*)d; p->zc_half = half;
+                } else {
+                    if (h) cudaFreeHost(h);
+                    cudaGetLastError();
+                }
+            }
+            if (p->h_zc) {
+                memcpy(p->h_zc, h_in, in_bytes);
+                if (exec_range(p, p->d_zc, p->d_zc + p->zc_half, p->batch) != 0) return -1;
+                CU(cudaStreamSynchronize(p->stream));
+                memcpy(h_out, p->h_zc + p->zc_half, out_bytes);
+                return 0;
+            }
+        }
+    }
     if (!p->d_ring[0]) {
         size_t target = 32u << 20;                       // bytes per chunk
         if (const char* e = getenv("FFTB200_CHUNK_MB")) target = (size_t)atol(e) << 20;
@@ -1101,6 +1132,7 @@ extern "C" void fftb200_plan_destroy(fftb200_plan* p) {
     if (p->work) cudaFree(p->work);
     if (p->chirp) cudaFree(p->chirp);
     if (p->fb) cudaFree(p->fb);
+    if (p->h_zc) cudaFreeHost(p->h_zc);
     for (int i = 0; i < fftb200_plan::NSTAGE; i++) {
         if (p->d_ring[i]) cudaFree(p->d_ring[i]);
         if (p->ev_up[i]) cudaEventDestroy(p->ev_up[i]);
