@@ -108,7 +108,7 @@ __global__ void __launch_bounds__(2 * PIPE_GROUP, 1) fft_pipe13_kernel(const Pip
     uint32_t round = 0;        // h / 3
     for (int h = g; h < my_halves; h += 2) {
         cd* const sm = bufs + (size_t)b * PIPE_TILE;
-        mbar_wait(&full[b + PIPE_STAGES * (round & 1)], (round >> 1) & 1);
+        mbar_wait_bounded(&full[b + PIPE_STAGES * (round & 1)], (round >> 1) & 1);   // a lost load traps instead of hanging the GPU
         cd x[16];
         // ---- sub-pass 0: radix 16, exact constants, in place ----
 #pragma unroll
