@@ -35,5 +35,7 @@ const KernelInfo* kernels_last(int* count);
 struct PipeArgs;
 const void* pipe_func(int logn, int inverse);                                  // nullptr if no variant
 void launch_pipe(int logn, const PipeArgs& a, int grid, cudaStream_t s);
+const void* pipe_real_func(int logn, int kind);                                // PIPE_R2C / PIPE_C2R variants (fft_pipe.cuh)
+void launch_pipe_real(int logn, int kind, const PipeArgs& a, int grid, cudaStream_t s);
 
 }  // namespace fftb200

@@ -11,6 +11,24 @@ static void launch_pipe_t(const PipeArgs& a, int grid, cudaStream_t s) {
 
 #define PIPE_CASES(X) X(9) X(10) X(11) X(12)
 
+// real-input / real-output variants (fft_plan_r2c_1d / fft_plan_c2r_1d for N = 512 .. 4096)
+const void* pipe_real_func(int logn, int kind) {
+    switch (logn) {
+#define X(L) case L: return kind == PIPE_R2C ? (const void*)fft_pipe_kernel<L, false, PIPE_R2C> : (const void*)fft_pipe_kernel<L, true, PIPE_C2R>;
+        PIPE_CASES(X)
+#undef X
+    }
+    return nullptr;
+}
+void launch_pipe_real(int logn, int kind, const PipeArgs& a, int grid, cudaStream_t s) {
+    switch (logn) {
+#define X(L) case L: if (kind == PIPE_R2C) fft_pipe_kernel<L, false, PIPE_R2C><<<grid, 2 * PIPE_GROUP, PIPE_SMEM, s>>>(a); \
+                     else fft_pipe_kernel<L, true, PIPE_C2R><<<grid, 2 * PIPE_GROUP, PIPE_SMEM, s>>>(a); break;
+        PIPE_CASES(X)
+#undef X
+    }
+}
+
 const void* pipe_func(int logn, int inverse) {
     switch (logn) {
 #define X(L) case L: return inverse ? (const void*)fft_pipe_kernel<L, true> : (const void*)fft_pipe_kernel<L, false>;

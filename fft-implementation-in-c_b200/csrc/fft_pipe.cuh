@@ -112,9 +112,17 @@ __device__ __forceinline__ cd cmulc(const cd a, const double c, const double d) 
     return make_double2(fma(a.x, c, -(a.y * d)), fma(a.x, d, a.y * c));
 }
 
-template <int LOGN, bool INV>
+// REAL = PIPE_R2C: the tile holds 4096 reals (promoted while gathering, fft_auto.c:394-397) and only the bins 0 .. N/2 are
+// stored, N/2 + 1 per transform (fft_auto.h:89-97) - the reference's promote-then-c2c reading of fft_plan_r2c_1d without
+// the promotion and extraction passes. REAL = PIPE_C2R (inverse only): the tile holds N/2 + 1 bins per transform, the
+// Hermitian half X[N - i] = conj(X[i]) is rebuilt while gathering and the real parts are stored (fft_auto.h:99-107).
+enum { PIPE_C2C = 0, PIPE_R2C = 1, PIPE_C2R = 2 };
+
+template <int LOGN, bool INV, int REAL = PIPE_C2C>
 __global__ void __launch_bounds__(2 * PIPE_GROUP, 1) fft_pipe_kernel(const PipeArgs a) {
     static_assert(LOGN >= 9 && LOGN <= 12, "one transform must be 512 .. 4096 points");
+    static_assert(REAL == PIPE_C2C || (REAL == PIPE_R2C && !INV) || (REAL == PIPE_C2R && INV), "r2c is forward, c2r inverse");
+    constexpr int NH = (1 << LOGN) / 2 + 1;   // bins per transform of a half spectrum
     constexpr int N = 1 << LOGN, NT = PIPE_TILE / N;  // transforms per tile
     constexpr int LR0 = LOGN - 8, R0 = 1 << LR0, NB0 = 16 / R0;
     constexpr int LN16 = LOGN - 4;                    // log2 (N / 16)
@@ -138,10 +146,11 @@ __global__ void __launch_bounds__(2 * PIPE_GROUP, 1) fft_pipe_kernel(const PipeA
         const long long tile = first + (long long)k * stride;
         long long nvalid = a.batch - tile * NT;
         if (nvalid > NT) nvalid = NT;
-        const uint32_t bytes = (uint32_t)nvalid * N * (uint32_t)sizeof(cd);
+        const uint32_t per = REAL == PIPE_R2C ? N * (uint32_t)sizeof(double) : REAL == PIPE_C2R ? NH * (uint32_t)sizeof(cd) : N * (uint32_t)sizeof(cd);
+        const uint32_t bytes = (uint32_t)nvalid * per;
         uint64_t* const bar = &full[b + PIPE_STAGES * (rnd & 1)];
         mbar_expect_tx(bar, bytes);
-        bulk_load(bufs + (size_t)b * PIPE_TILE, a.in + tile * PIPE_TILE, bytes, bar);
+        bulk_load(bufs + (size_t)b * PIPE_TILE, reinterpret_cast<const char*>(a.in) + (size_t)tile * NT * per, bytes, bar);
     };
 
     if (threadIdx.x == 0) {
@@ -186,10 +195,22 @@ __global__ void __launch_bounds__(2 * PIPE_GROUP, 1) fft_pipe_kernel(const PipeA
         // ---- sub-pass 0: radix R0, exact constants, in place (each thread owns idx = t + 256 e) ----
 #pragma unroll
         for (int e = 0; e < 16; e++) {
-            cd y = sm[t + 256 * e];
-            if (INV) y.y = -y.y;
+            cd y;
+            if constexpr (REAL == PIPE_R2C) {
+                y = make_double2(reinterpret_cast<const double*>(sm)[t + 256 * e], 0.0);
+            } else if constexpr (REAL == PIPE_C2R) {
+                // element i of transform jj: bin i for i <= N/2, conj(bin N - i) above; conjugated once more for the inverse
+                const int idx = t + 256 * e, jj = idx >> LOGN, i = idx & (N - 1);
+                const bool up = i > N / 2;
+                y = sm[jj * NH + (up ? N - i : i)];
+                if (!up) y.y = -y.y;
+            } else {
+                y = sm[t + 256 * e];
+                if (INV) y.y = -y.y;
+            }
             x[(e / R0) * R0 + bitrev_c<LR0>(e % R0)] = y;
         }
+        if constexpr (REAL != PIPE_C2C) group_sync(g);   // the complex tile overwrites other threads' packed inputs: gather everything first
 #pragma unroll
         for (int bb = 0; bb < NB0; bb++) SubStageExact<LR0, 1, 0, 0>::run(&x[bb * R0]);
         __syncwarp();  // the swizzle moves a thread's slots within its warp's 32-element rows
@@ -231,13 +252,29 @@ __global__ void __launch_bounds__(2 * PIPE_GROUP, 1) fft_pipe_kernel(const PipeA
         {
             const long long tile = first + (long long)k * stride;
             const bool valid = tile * NT + j < a.batch;
-            cd* p = a.out + tile * PIPE_TILE + wr1;
-            if (valid) {
+            if constexpr (REAL == PIPE_R2C) {
+                // bins k = v + (q << LN16) <= N/2: q < 8, and the Nyquist bin (q = 8, v = 0)
+                cd* p = a.out + (size_t)(tile * NT + j) * NH + v;
+                if (valid) {
 #pragma unroll
-                for (int q = 0; q < 16; q++) {
-                    cd r = x[q];
-                    if (INV) { r.x *= sc; r.y *= -sc; }
-                    p[q << LN16] = r;
+                    for (int q = 0; q < 8; q++) p[q << LN16] = x[q];
+                    if (v == 0) p[8 << LN16] = x[8];
+                }
+            } else if constexpr (REAL == PIPE_C2R) {
+                double* p = reinterpret_cast<double*>(a.out) + tile * PIPE_TILE + wr1;
+                if (valid) {
+#pragma unroll
+                    for (int q = 0; q < 16; q++) p[q << LN16] = x[q].x * sc;
+                }
+            } else {
+                cd* p = a.out + tile * PIPE_TILE + wr1;
+                if (valid) {
+#pragma unroll
+                    for (int q = 0; q < 16; q++) {
+                        cd r = x[q];
+                        if (INV) { r.x *= sc; r.y *= -sc; }
+                        p[q << LN16] = r;
+                    }
                 }
             }
         }

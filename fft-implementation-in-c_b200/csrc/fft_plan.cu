@@ -258,6 +258,7 @@ struct fftb200_plan {
     int peer_lw = 0, peer_lrows = 0, peer_lg = 0, peer_me = 0;
     double scale = 0.0;        // 1/m, or the caller's value for partial plans of a distributed transform
     cd* work = nullptr;        // Bluestein / R2C: padded complex work array, m * batch
+    bool pipe_real = false;    // R2C / C2R of 512 .. 4096 points: the pipe kernel reads reals / half spectra itself (no work array)
     cd* chirp = nullptr;       // Bluestein: n entries
     cd* fb = nullptr;          // Bluestein: FFT_m of the wrapped chirp
     // host staging (exec_host)
@@ -756,12 +757,21 @@ extern "C" int fftb200_plan_create(fftb200_plan** out, const fftb200_plan_desc* 
                 if (cudaFuncSetAttribute(fused_r2c_func(p->passes[0].fused_lm, p->passes[0].fused_lr), cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)FUSED_SMEM) != cudaSuccess) { rc = fail("cudaFuncSetAttribute failed"); break; }
                 p->desc += " [real in, half spectrum out, no promote / extract passes]";
+            } else if (p->passes.size() == 1 && !p->passes[0].k && p->passes[0].log_p <= 12 && !getenv("FFTB200_NO_PIPE_REAL")) {
+                if (cudaFuncSetAttribute(pipe_real_func(p->passes[0].log_p, PIPE_R2C), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PIPE_SMEM) != cudaSuccess) { rc = fail("cudaFuncSetAttribute failed"); break; }
+                p->pipe_real = true;
+                p->desc += " [real in, half spectrum out, no promote / extract passes]";
             } else {
                 p->work = (cd*)fftb200_malloc(sizeof(cd) * (size_t)p->m * (size_t)p->batch);
                 if (!p->work) { rc = -1; break; }
                 p->launches += 2;
             }
         }
+        if (d->kind == FFTB200_C2R && p->passes.size() == 1 && !p->passes[0].k && !p->passes[0].fused_lm && p->passes[0].log_p <= 12 && !getenv("FFTB200_NO_PIPE_REAL")) {
+            if (cudaFuncSetAttribute(pipe_real_func(p->passes[0].log_p, PIPE_C2R), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PIPE_SMEM) != cudaSuccess) { rc = fail("cudaFuncSetAttribute failed"); break; }
+            p->pipe_real = true;
+            p->desc += " [half spectrum in, real out, no extension / extraction passes]";
+        } else
         if (d->kind == FFTB200_C2R) {
             // Hermitian extension -> inverse c2c of the full length with the reference's stage operators -> real parts
             p->work = (cd*)fftb200_malloc(sizeof(cd) * (size_t)p->m * (size_t)p->batch);
@@ -982,6 +992,18 @@ static int exec_range(fftb200_plan* p, const void* d_in, void* d_out, long long 
     const int inverse = p->dir > 0;
     if (p->kind == FFTB200_C2C) return enqueue_c2c(p, (const cd*)d_in, (cd*)d_out, inverse, nbatch);
     const size_t m = (size_t)p->m, n = (size_t)p->n, total = m * (size_t)nbatch;
+    if (p->pipe_real) {
+        if (nbatch <= 0) return 0;
+        const Pass& ps = p->passes[0];
+        const long long ntiles = pass_tiles(ps, nbatch);
+        PipeArgs pa;
+        pa.in = (const cd*)d_in; pa.out = (cd*)d_out; pa.tab = p->acc;
+        pa.ntiles = ntiles; pa.batch = nbatch;
+        pa.inverse = p->kind == FFTB200_C2R; pa.scale = p->scale;
+        launch_pipe_real(ps.log_p, p->kind == FFTB200_R2C ? PIPE_R2C : PIPE_C2R, pa, (int)(ntiles < ps.grid_max ? ntiles : ps.grid_max), p->stream);
+        CU(cudaGetLastError());
+        return 0;
+    }
     if (p->kind == FFTB200_C2R) {
         if (nbatch <= 0) return 0;
         const size_t nh = n / 2 + 1;
@@ -1053,7 +1075,7 @@ extern "C" int fftb200_plan_exec_host(fftb200_plan* p, const void* h_in, void* h
     const size_t in_per = p->kind == FFTB200_R2C ? sizeof(double) * (size_t)p->n : p->kind == FFTB200_C2R ? half : sizeof(cd) * (size_t)p->n;  // bytes / transform
     const size_t out_per = p->kind == FFTB200_R2C ? half : p->kind == FFTB200_C2R ? sizeof(double) * (size_t)p->n : sizeof(cd) * (size_t)p->n;
     // the fused r2c kernel cannot run in place: its staging buffers hold the real input followed by the half spectra
-    const bool split = p->kind == FFTB200_R2C && !p->work;
+    const bool split = (p->kind == FFTB200_R2C || p->kind == FFTB200_C2R) && !p->work;   // (and neither can the real variants of the pipe kernel)
     const size_t per = split ? in_per + out_per + 16 : (in_per > out_per ? in_per : out_per);
     // Small single-kernel transforms (fft_auto on 1024 points: BASELINE config 1) are latency, not bandwidth: two cudaMemcpy
     // calls and three streams cost ~40 us around a 9 us kernel. Instead the caller's data goes through a page-locked, device-

@@ -39,6 +39,40 @@ def test_c2r_batched_engine_plan(gpu, port, O, n, batch):
     L.fftb200_plan_destroy(plan)
 
 
+@pytest.mark.parametrize("n,batch", [(512, 1), (512, 1187), (1024, 5), (2048, 300), (4096, 1), (4096, 301)])
+def test_real_variants_of_the_pipe_kernel(gpu, port, O, n, batch, monkeypatch):
+    """Batched r2c / c2r of 512 .. 4096 points run in fft_pipe_kernel's real variants (reals / half spectra read and written by
+    the kernel itself); FFTB200_NO_PIPE_REAL=1 is promote - c2c - extract (r2c) and extend - inverse c2c - real parts (c2r).
+    The arithmetic is the same: bit-identical, and equal to the oracle. Batches ragged against the 4096-point tiles."""
+    import torch
+    L = gpu.lib
+    x = port.fill(75, 0, n * batch).real.copy().reshape(batch, n)
+    xd = torch.from_numpy(x).cuda()
+
+    def run():
+        fwd = gpu.engine_plan(n, batch, gpu.FFTB200_R2C)
+        inv = gpu.engine_plan(n, batch, gpu.FFTB200_C2R, direction=1)
+        desc = L.fftb200_plan_describe(fwd) + L.fftb200_plan_describe(inv)
+        hd = torch.zeros((batch, n // 2 + 1), dtype=torch.complex128, device="cuda")
+        yd = torch.zeros((batch, n), dtype=torch.float64, device="cuda")
+        for _ in range(2):
+            assert L.fftb200_plan_exec(fwd, xd.data_ptr(), hd.data_ptr()) == 0
+            assert L.fftb200_plan_exec(inv, hd.data_ptr(), yd.data_ptr()) == 0
+        L.fftb200_plan_destroy(fwd)
+        L.fftb200_plan_destroy(inv)
+        return hd.cpu().numpy(), yd.cpu().numpy(), desc
+    h1, y1, d1 = run()
+    assert b"no promote" in d1 and b"no extension" in d1
+    monkeypatch.setenv("FFTB200_NO_PIPE_REAL", "1")
+    h2, y2, d2 = run()
+    monkeypatch.delenv("FFTB200_NO_PIPE_REAL")
+    assert b"hermitian extension" in d2
+    assert np.array_equal(h1, h2) and np.array_equal(y1, y2)
+    rows = sorted({0, batch // 2, batch - 1})
+    assert O.rel_l2(h1[rows], np.stack([port.r2c(x[r]) for r in rows])) <= TOL
+    assert O.rel_l2(y1, x) <= TOL
+
+
 SHAPES = [(64, 128), (256, 64), (8, 32), (1024, 128), (2, 2), (1, 64), (64, 1), (32, 4096), (4096, 32), (512, 512),
           (2048, 1024), (16, 16), (128, 4)]
 
