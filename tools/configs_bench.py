@@ -77,3 +77,17 @@ best, med = time_engine(p, din, dout)
 print(json.dumps({"cfg": "5: r2c n=2^20 x 256", "ms_best": round(best, 4), "algorithmic_GBps(8n+16(n/2+1))": round((8 * n + 16 * (n // 2 + 1)) * b / best * 1e-6),
                   "gflops(2.5 n log2 n)": round(2.5 * n * 20 * b / best * 1e-6), "plan": L.fftb200_plan_describe(p).decode()}), flush=True)
 L.fftb200_plan_destroy(p)
+L.fftb200_free(din); L.fftb200_free(dout)
+# the real transforms either side of config 5: r2c / c2r at 4096 (inside the pipe kernel) and c2r at 2^20
+for lg, kinds in ((12, (F.FFTB200_R2C, F.FFTB200_C2R)), (20, (F.FFTB200_C2R,))):
+    n = 1 << lg; b = (1 << 28) >> lg; nh = n // 2 + 1
+    dre = L.fftb200_malloc(8 * n * b); dcx = L.fftb200_malloc(16 * nh * b)
+    L.fftb200_fill_splitmix(dre, 47, 0, n * b // 2); L.fftb200_fill_splitmix(dcx, 48, 0, nh * b)
+    for kind in kinds:
+        p = F.engine_plan(n, b, kind, -1 if kind == F.FFTB200_R2C else 1)
+        din, dout = (dre, dcx) if kind == F.FFTB200_R2C else (dcx, dre)
+        best, med = time_engine(p, din, dout)
+        print(json.dumps({"cfg": "%s n=2^%d x %d" % ("r2c" if kind == F.FFTB200_R2C else "c2r", lg, b), "ms_best": round(best, 4),
+                          "algorithmic_GBps(8n+16(n/2+1))": round((8 * n + 16 * nh) * b / best * 1e-6), "plan": L.fftb200_plan_describe(p).decode()}), flush=True)
+        L.fftb200_plan_destroy(p)
+    L.fftb200_free(dre); L.fftb200_free(dcx)
