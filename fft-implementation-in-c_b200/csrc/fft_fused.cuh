@@ -305,13 +305,16 @@ __device__ __forceinline__ void fused_publish(int* counter) {
 // R2C (forward only): the input is real (n doubles per transform, promoted in the first gather) and only the bins
 // 0 .. n/2 are stored (n/2 + 1 per transform, fft_auto.h:89-97) - the reference's promote-then-c2c reading of
 // fft_plan_r2c_1d without the separate promotion and extraction passes.
-template <int LM, int LR, bool INV, bool COLS = false, bool R2C = false>
+// C2R (inverse only): the input is the Hermitian-extended spectrum (c2r_expand_kernel), only the real parts of the result are
+// staged and stored (n doubles per transform, fft_auto.h:99-107): the separate real-part pass and its 24 bytes per point go away.
+template <int LM, int LR, bool INV, bool COLS = false, bool R2C = false, bool C2R = false>
 __global__ void __launch_bounds__(FUSED_THREADS, 1)
 fft_fused_kernel(const FusedArgs a, const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUtensorMap tm_sc,
                  const __grid_constant__ CUtensorMap tm_out) {
     static_assert(LM >= 6 && LM <= 10 && LR >= 6 && LR <= 10, "pass sizes 64 .. 1024");
     static_assert(!COLS || (LM == 8 && LR == 8), "column mode is built for 256 x 256");
     static_assert(!R2C || (!INV && !COLS), "r2c is a forward transform of whole arrays");
+    static_assert(!C2R || (INV && !COLS && !R2C), "c2r is an inverse transform of whole arrays");
     constexpr int LOGN = COLS ? 20 : LM + LR;             // points per (virtual) transform
     constexpr int LOG_TPT = LOGN - 12;
     constexpr int LC = 12 - LM, LC2 = 12 - LR;          // log2 columns per A tile / k's per B tile
@@ -323,7 +326,7 @@ fft_fused_kernel(const FusedArgs a, const __grid_constant__ CUtensorMap tm_in, c
     // the store drain into the compute group's time. Same-box A/B at 2^28 points (ms, direct vs staged): 2^13 2.61 / 2.24,
     // 2^14 2.34 / 2.62, 2^15 2.34 / 2.59, 2^16 2.35 / 2.26, 2^17 2.55 / 2.50, 2^18 3.04 / 2.77, 2^19 3.00 / 2.79,
     // 2^20 3.39 / 2.95: it pays only for LR = 7 (rows of 32 elements, two sub-passes), which is where it is used.
-    constexpr bool BDIRECT = FUSED_BDIRECT && !COLS && !R2C && LR == 7;
+    constexpr bool BDIRECT = FUSED_BDIRECT && !COLS && !R2C && !C2R && LR == 7;
 
     extern __shared__ __align__(128) unsigned char smem_raw[];
     cd* const bufs = reinterpret_cast<cd*>(smem_raw);
@@ -458,6 +461,8 @@ fft_fused_kernel(const FusedArgs a, const __grid_constant__ CUtensorMap tm_in, c
                         if constexpr (R2C) {   // rows q < R/2 (bins below n/2) are the first two quarters; then the Nyquist bin X[M R/2]
                             if (q < 2) tma_store_3d(&tm_out, 2 * (blk << LC2), q * (QT >> LC2), (int)tr, buf + q * QT, pol_first);
                             else if (q == 2 && blk == 0) bulk_store(a.out + (size_t)tr * ((1 << (LOGN - 1)) + 1) + (1 << (LOGN - 1)), buf + 2 * QT, sizeof(cd));
+                        } else if constexpr (C2R) {   // real rows: a quarter is 1024 doubles
+                            tma_store_2d(&tm_out, blk << LC2, (int)((tr << LR) + q * (QT >> LC2)), reinterpret_cast<double*>(buf) + q * QT, pol_first);
                         } else if constexpr (COLS)   // [b][q][k_hi][c]
                             tma_store_4d(&tm_out, 32 * (int)(tr & ((1 << a.log_cb) - 1)), blk, q * 64, (int)(tr >> a.log_cb), buf + q * QT, pol_first);
                         else
@@ -680,12 +685,18 @@ fft_fused_kernel(const FusedArgs a, const __grid_constant__ CUtensorMap tm_in, c
                 }
             } else {
                 group_sync(g2);   // every gather is done: stage X[k + M q] in place as [q][k], the box the tensor store expects
-                cd* p = sm + gl.hi + (gl.kloc << LC2);
+                if constexpr (C2R) {
+                    double* p = reinterpret_cast<double*>(sm) + gl.hi + (gl.kloc << LC2);
 #pragma unroll
-                for (int q = 0; q < 16; q++) {
-                    cd r = x[q];
-                    if (INV) { r.x *= sc; r.y *= -sc; }
-                    p[q << (AL + LC2)] = r;
+                    for (int q = 0; q < 16; q++) p[q << (AL + LC2)] = x[q].x * sc;
+                } else {
+                    cd* p = sm + gl.hi + (gl.kloc << LC2);
+#pragma unroll
+                    for (int q = 0; q < 16; q++) {
+                        cd r = x[q];
+                        if (INV) { r.x *= sc; r.y *= -sc; }
+                        p[q << (AL + LC2)] = r;
+                    }
                 }
                 fused_stage_done(&staged[b], t);
             }
@@ -718,6 +729,17 @@ const void* fused_r2c_func_0(int lm, int lr);
 const void* fused_r2c_func_1(int lm, int lr);
 const void* fused_r2c_func_2(int lm, int lr);
 const void* fused_r2c_func_3(int lm, int lr);
+const void* fused_c2r_func_0(int lm, int lr);
+const void* fused_c2r_func_1(int lm, int lr);
+const void* fused_c2r_func_2(int lm, int lr);
+const void* fused_c2r_func_3(int lm, int lr);
+inline const void* fused_c2r_func(int lm, int lr) {
+    const void* f = fused_c2r_func_0(lm, lr);
+    if (!f) f = fused_c2r_func_1(lm, lr);
+    if (!f) f = fused_c2r_func_2(lm, lr);
+    if (!f) f = fused_c2r_func_3(lm, lr);
+    return f;
+}
 inline const void* fused_r2c_func(int lm, int lr) {
     const void* f = fused_r2c_func_0(lm, lr);
     if (!f) f = fused_r2c_func_1(lm, lr);

@@ -8,6 +8,12 @@ const void* fused_func_3(int lm, int lr, int inverse) {
 #undef X
     return nullptr;
 }
+const void* fused_c2r_func_3(int lm, int lr) {
+#define X(A, B) if (lm == A && lr == B) return (const void*)fft_fused_kernel<A, B, true, false, false, true>;
+    FUSED_PAIRS(X)
+#undef X
+    return nullptr;
+}
 const void* fused_r2c_func_3(int lm, int lr) {
 #define X(A, B) if (lm == A && lr == B) return (const void*)fft_fused_kernel<A, B, false, false, true>;
     FUSED_PAIRS(X)

@@ -258,6 +258,7 @@ struct fftb200_plan {
     int peer_lw = 0, peer_lrows = 0, peer_lg = 0, peer_me = 0;
     double scale = 0.0;        // 1/m, or the caller's value for partial plans of a distributed transform
     cd* work = nullptr;        // Bluestein / R2C: padded complex work array, m * batch
+    bool fused_c2r = false;    // C2R of 2^14 .. 2^20 points: the fused kernel stores the real parts itself
     bool pipe_real = false;    // R2C / C2R of 512 .. 4096 points: the pipe kernel reads reals / half spectra itself (no work array)
     cd* chirp = nullptr;       // Bluestein: n entries
     cd* fb = nullptr;          // Bluestein: FFT_m of the wrapped chirp
@@ -496,7 +497,7 @@ static int enqueue_fused(fftb200_plan* p, const Pass& ps, const cd* in, cd* out,
     if (const char* e = getenv("FFTB200_FUSED_PROMO")) promo = atoi(e);
     const CUtensorMapL2promotion pr = promo >= 2 ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B : promo == 1 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B
                                                                                                    : CU_TENSOR_MAP_L2_PROMOTION_NONE;
-    if (r2c) {
+    if (r2c == 1) {
         // real input rows of R doubles; output bins 0 .. n/2 - 1 as [b][q < R/2][k] with n/2 + 1 elements per transform
         const cuuint64_t gdim[2] = {(cuuint64_t)1 << lr, (cuuint64_t)nbatch << lm};
         const cuuint64_t gstr[1] = {(cuuint64_t)sizeof(double) << lr};
@@ -513,7 +514,7 @@ static int enqueue_fused(fftb200_plan* p, const Pass& ps, const cd* in, cd* out,
         if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled failed (%d) for the half spectrum", (int)r);
     }
     for (int i = 0; i < 3 && !cols; i++) {
-        if (r2c && i != 1) continue;
+        if (r2c == 1 && i != 1) continue;
         const int lcols = i == 2 ? lm : lr, lrows = i == 2 ? lr : lm;          // row length / rows per transform (log2)
         const long long ntr = i == 1 ? slots * gt : nbatch;
         void* base = i == 0 ? (void*)in : i == 1 ? (void*)p->fscratch : (void*)out;
@@ -524,6 +525,16 @@ static int enqueue_fused(fftb200_plan* p, const Pass& ps, const cd* in, cd* out,
         const CUresult r = enc(&tm[i], CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, base, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                                CU_TENSOR_MAP_SWIZZLE_NONE, i == 0 ? pr : CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled failed (%d) for map %d", (int)r, i);
+    }
+    if (r2c == 2) {
+        // c2r: the output as real rows [nbatch * R][M doubles], a quarter of a pass-B tile is the box C2 x R/4
+        const cuuint64_t odim[2] = {(cuuint64_t)1 << lm, (cuuint64_t)nbatch << lr};
+        const cuuint64_t ostr[1] = {(cuuint64_t)sizeof(double) << lm};
+        const cuuint32_t obox[2] = {(cuuint32_t)1 << (12 - lr), (cuuint32_t)1 << (lr - 2)};
+        const cuuint32_t estr[2] = {1, 1};
+        const CUresult r = enc(&tm[2], CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, (void*)out, odim, ostr, obox, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled failed (%d) for the real output", (int)r);
     }
     for (int i = 0; i < 3 && cols; i++) {
         // input / output: [b][t_hi or q][t_lo or k_hi][c] with rows of 2^log_rw columns; scratch ring: [slot][k_hi][t_lo][c16]
@@ -552,7 +563,7 @@ static int enqueue_fused(fftb200_plan* p, const Pass& ps, const cd* in, cd* out,
 #endif
     const long long items = 2 * nbatch * tpt;
     const int grid = (int)(items < ps.grid_max ? items : ps.grid_max);
-    const void* func = r2c ? fused_r2c_func(lm, lr) : cols ? fused_cols_func(inverse) : fused_func(lm, lr, inverse);
+    const void* func = r2c == 1 ? fused_r2c_func(lm, lr) : r2c == 2 ? fused_c2r_func(lm, lr) : cols ? fused_cols_func(inverse) : fused_func(lm, lr, inverse);
     if (!func) return fail("no fused kernel for 2^%d x 2^%d", lm, lr);
     CU(launch_fused(func, fa, tm, grid, p->stream));
 #ifdef FUSED_PROF
@@ -776,8 +787,17 @@ extern "C" int fftb200_plan_create(fftb200_plan** out, const fftb200_plan_desc* 
             // Hermitian extension -> inverse c2c of the full length with the reference's stage operators -> real parts
             p->work = (cd*)fftb200_malloc(sizeof(cd) * (size_t)p->m * (size_t)p->batch);
             if (!p->work) { rc = -1; break; }
-            p->launches += 2;
-            p->desc += " [hermitian extension + inverse c2c + real parts]";
+            p->fused_c2r = p->passes.size() == 1 && p->passes[0].fused_lm && !getenv("FFTB200_NO_FUSED_C2R") &&
+                           fused_c2r_func(p->passes[0].fused_lm, p->passes[0].fused_lr);
+            if (p->fused_c2r) {
+                if (cudaFuncSetAttribute(fused_c2r_func(p->passes[0].fused_lm, p->passes[0].fused_lr), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)FUSED_SMEM) != cudaSuccess) { rc = fail("cudaFuncSetAttribute failed"); break; }
+                p->launches += 1;
+                p->desc += " [hermitian extension + inverse c2c storing the real parts]";
+            } else {
+                p->launches += 2;
+                p->desc += " [hermitian extension + inverse c2c + real parts]";
+            }
         }
         if (d->kind == FFTB200_BLUESTEIN) {
             const size_t m = (size_t)p->m;
@@ -1008,6 +1028,11 @@ static int exec_range(fftb200_plan* p, const void* d_in, void* d_out, long long 
         if (nbatch <= 0) return 0;
         const size_t nh = n / 2 + 1;
         c2r_expand_kernel<<<grid_for(total), 256, 0, p->stream>>>(p->work, (const cd*)d_in, n, nh, total);
+        if (p->fused_c2r) {
+            if (enqueue_fused(p, p->passes[0], p->work, (cd*)d_out, 1, nbatch, 2) != 0) return -1;
+            CU(cudaGetLastError());
+            return 0;
+        }
         if (enqueue_c2c(p, p->work, p->work, 1, nbatch) != 0) return -1;
         c2r_real_kernel<<<grid_for(total), 256, 0, p->stream>>>((double*)d_out, p->work, total);
         CU(cudaGetLastError());

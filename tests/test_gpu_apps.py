@@ -73,6 +73,35 @@ def test_real_variants_of_the_pipe_kernel(gpu, port, O, n, batch, monkeypatch):
     assert O.rel_l2(y1, x) <= TOL
 
 
+@pytest.mark.parametrize("n,batch", [(1 << 14, 1), (1 << 14, 77), (1 << 15, 40), (1 << 16, 9), (1 << 17, 5), (1 << 18, 3), (1 << 19, 2), (1 << 20, 2)])
+def test_c2r_fused_kernel_stores_real_parts(gpu, port, O, n, batch, monkeypatch):
+    """c2r of 2^14 .. 2^20 points: the fused inverse kernel stages and stores only the real parts (fft_fused.cuh, C2R);
+    FFTB200_NO_FUSED_C2R=1 keeps the separate real-part pass. Same arithmetic: bit-identical; first / last rows vs the oracle."""
+    import torch
+    L = gpu.lib
+    x = port.fill(76, 0, n * batch).real.copy().reshape(batch, n)
+    half = np.fft.rfft(x, axis=1)
+    hd = torch.from_numpy(half).cuda()
+
+    def run():
+        plan = gpu.engine_plan(n, batch, gpu.FFTB200_C2R, direction=1)
+        desc = L.fftb200_plan_describe(plan)
+        yd = torch.zeros((batch, n), dtype=torch.float64, device="cuda")
+        for _ in range(2):
+            assert L.fftb200_plan_exec(plan, hd.data_ptr(), yd.data_ptr()) == 0
+        L.fftb200_plan_destroy(plan)
+        return yd.cpu().numpy(), desc
+    y1, d1 = run()
+    assert b"storing the real parts" in d1
+    monkeypatch.setenv("FFTB200_NO_FUSED_C2R", "1")
+    y2, d2 = run()
+    monkeypatch.delenv("FFTB200_NO_FUSED_C2R")
+    assert b"+ real parts" in d2
+    assert np.array_equal(y1, y2)
+    rows = sorted({0, batch - 1})
+    assert O.rel_l2(y1[rows], np.stack([port.c2r(half[r], n) for r in rows])) <= TOL
+
+
 SHAPES = [(64, 128), (256, 64), (8, 32), (1024, 128), (2, 2), (1, 64), (64, 1), (32, 4096), (4096, 32), (512, 512),
           (2048, 1024), (16, 16), (128, 4)]
 
