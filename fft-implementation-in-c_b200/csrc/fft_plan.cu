@@ -26,6 +26,7 @@
 #include "fft_fused.cuh"
 #include "fft_pipe.cuh"
 #include "fft_pipe13.cuh"
+#include "fft_lastpipe.cuh"
 
 using namespace fftb200;
 
@@ -225,6 +226,7 @@ struct Pass {
     const KernelInfo* k;   // nullptr: persistent TMA kernel fft_pipe_kernel<log_p>, or the fused kernel when fused_lm > 0
     int fused_lm = 0, fused_lr = 0;   // fft_fused_kernel<fused_lm, fused_lr>: both passes in one launch
     int fused_cols = 0;               // column mode: stages 1 .. 16 of a larger transform, rows of 2^(log_n - 16) columns
+    int lastpipe = 0;                 // LAST tile pass with a TMA-ring twin (fft_lastpipe.cuh), used when nothing rides on the pass
     int log_p;
     int log_m;
     int nt;        // whole-transform kernels: transforms per tile (tiles = ceil(nbatch / nt)); else 0
@@ -428,6 +430,21 @@ static int build_passes(fftb200_plan* p, DeviceState* ds) {
         p->desc += b;
         log_m += lp;
     }
+    return 0;
+}
+
+// The last pass of a multi-pass plan also exists as a persistent TMA-ring kernel (fft_lastpipe.cuh); the tile kernel stays for the
+// executions where something rides on the pass (Bluestein factors, peer stores of the distributed transform).
+static int mark_lastpipe(fftb200_plan* p, DeviceState* ds) {
+    if (p->passes.size() < 2 || getenv("FFTB200_NO_LASTPIPE")) return 0;
+    Pass& ps = p->passes.back();
+    if (!ps.k || ps.k->mode != MODE_LAST || !ps.final_pass) return 0;
+    // same-box A/B at 2^28 points (ms, ring / tile kernel): 2^21 4.03 / 4.04, 2^22 3.89 / 3.93, 2^23 3.96 / 4.30, 2^24 4.18 / 4.32, 2^25 4.82 / 4.61
+    if (ps.log_p < 6 || ps.log_p > 8 || !lastpipe_func(ps.log_p, 0)) return 0;
+    for (int iv = 0; iv < 2; iv++)
+        CU(cudaFuncSetAttribute(lastpipe_func(ps.log_p, iv), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LASTPIPE_SMEM));
+    ps.lastpipe = ds->sms;
+    p->desc += "[tma ring]";
     return 0;
 }
 
@@ -652,9 +669,18 @@ static int enqueue_c2c(fftb200_plan* p, const cd* in, cd* out, int inverse, long
             launch_pipe(ps.log_p, pa, grid, p->stream);
             continue;
         }
-        TileArgs a;
         const cd* src = ps.src == BUF_IN ? in : ps.src == BUF_OUT ? out : p->scratch;
         cd* dst = ps.dst == BUF_OUT ? out : p->scratch;
+        if (ps.lastpipe && !post && !p->peers) {
+            LastPipeArgs la;
+            la.in = src; la.out = dst; la.tab = p->tab;
+            la.batch = nbatch; la.log_n = p->log_n; la.log_m = ps.log_m;
+            la.ntiles = nbatch << (ps.log_m - (12 - ps.log_p));
+            la.inverse = inverse; la.scale = p->scale;
+            CU(launch_lastpipe(ps.log_p, la, (int)(la.ntiles < ps.lastpipe ? la.ntiles : ps.lastpipe), p->stream));
+            continue;
+        }
+        TileArgs a;
         a.in = src; a.out = dst; a.tab = p->tab;
         a.ntiles = ntiles; a.batch = nbatch;
         a.log_n = p->log_n; a.log_m = ps.log_m;
@@ -745,6 +771,7 @@ extern "C" int fftb200_plan_create(fftb200_plan** out, const fftb200_plan_desc* 
         snprintf(head, sizeof(head), "%s n=%d b=%d dir=%d: ", d->kind == FFTB200_C2C ? "c2c" : d->kind == FFTB200_R2C ? "r2c" : d->kind == FFTB200_C2R ? "c2r" : "bluestein", d->n, d->batch, d->direction);
         p->desc = head;
         if ((rc = build_passes(p, ds)) != 0) break;
+        if ((rc = mark_lastpipe(p, ds)) != 0) break;
         p->launches = (int)p->passes.size();
         if (!p->passes.empty() && p->passes[0].fused_lm) {
             // dtw[j][h] = table entry (h << a_tot_j) - 1: stage a_tot_j + s, index q << a_tot_j, h = 2^(s-1) + q

@@ -349,6 +349,25 @@ def test_small_host_transforms_zero_copy_equals_staged(gpu, port, O, n, monkeypa
     assert O.rel_l2(a[0], port.fft(x, -1)) <= TOL
 
 
+@pytest.mark.parametrize("log_n,batch", [(22, 3), (23, 2), (24, 1)])
+@pytest.mark.parametrize("direction", [-1, 1])
+def test_tma_ring_last_pass_equals_tile_last_pass(gpu, port, O, log_n, batch, direction, monkeypatch):
+    """N = 2^22 .. 2^24: the last pass runs in fft_lastpipe_kernel (TMA ring, the fused kernel's pass-B dataflow);
+    FFTB200_NO_LASTPIPE=1 keeps fft_tile_kernel<LAST>. Same table twiddles and butterflies: bit-identical where the radix
+    split is the same (2^23, 2^24), within 1e-15 otherwise; last transform against the oracle."""
+    n = 1 << log_n
+    x = port.fill(55, 0, n * batch).reshape(batch, n)
+    y = gpu.gpu_fft_batch(x, direction)
+    monkeypatch.setenv("FFTB200_NO_LASTPIPE", "1")
+    z = gpu.gpu_fft_batch(x, direction)
+    monkeypatch.delenv("FFTB200_NO_LASTPIPE")
+    if log_n >= 23:
+        assert np.array_equal(y, z)
+    else:
+        assert O.rel_l2(y, z) <= 1e-15
+    assert O.rel_l2(y[-1:], port.fft_batch(x[-1:], direction)) <= TOL
+
+
 def test_two_fused_plans_run_concurrently(gpu, port, O):
     """The fused kernel's CTAs synchronise through global counters and must all be resident; it is launched
     cooperatively, so two plans enqueued back to back on their own streams must both finish with the right answer."""
