@@ -14,7 +14,8 @@ static void launch_pipe_t(const PipeArgs& a, int grid, cudaStream_t s) {
 // real-input / real-output variants (fft_plan_r2c_1d / fft_plan_c2r_1d for N = 512 .. 4096)
 const void* pipe_real_func(int logn, int kind) {
     switch (logn) {
-#define X(L) case L: return kind == PIPE_R2C ? (const void*)fft_pipe_kernel<L, false, PIPE_R2C> : (const void*)fft_pipe_kernel<L, true, PIPE_C2R>;
+#define X(L) case L: return kind == PIPE_R2C ? (const void*)fft_pipe_kernel<L, false, PIPE_R2C> : kind == PIPE_C2R ? (const void*)fft_pipe_kernel<L, true, PIPE_C2R> \
+                          : kind == PIPE_BLUE_FWD ? (const void*)fft_pipe_kernel<L, false, PIPE_BLUE_FWD> : (const void*)fft_pipe_kernel<L, true, PIPE_BLUE_INV>;
         PIPE_CASES(X)
 #undef X
     }
@@ -23,7 +24,9 @@ const void* pipe_real_func(int logn, int kind) {
 void launch_pipe_real(int logn, int kind, const PipeArgs& a, int grid, cudaStream_t s) {
     switch (logn) {
 #define X(L) case L: if (kind == PIPE_R2C) fft_pipe_kernel<L, false, PIPE_R2C><<<grid, 2 * PIPE_GROUP, PIPE_SMEM, s>>>(a); \
-                     else fft_pipe_kernel<L, true, PIPE_C2R><<<grid, 2 * PIPE_GROUP, PIPE_SMEM, s>>>(a); break;
+                     else if (kind == PIPE_C2R) fft_pipe_kernel<L, true, PIPE_C2R><<<grid, 2 * PIPE_GROUP, PIPE_SMEM, s>>>(a); \
+                     else if (kind == PIPE_BLUE_FWD) fft_pipe_kernel<L, false, PIPE_BLUE_FWD><<<grid, 2 * PIPE_GROUP, PIPE_SMEM, s>>>(a); \
+                     else fft_pipe_kernel<L, true, PIPE_BLUE_INV><<<grid, 2 * PIPE_GROUP, PIPE_SMEM, s>>>(a); break;
         PIPE_CASES(X)
 #undef X
     }

@@ -43,6 +43,11 @@ struct PipeArgs {
     long long batch;
     int inverse;
     double scale;      // 1/N, applied when inverse
+    // Bluestein variants (bluestein.c:107-148): chirp of the caller's length n_user, spectrum FB of the wrapped chirp (N entries)
+    const cd* chirp;
+    const cd* fb;
+    int n_user;
+    double y_scale;    // 1/n for the inverse direction of the caller's transform, else 1
 };
 
 constexpr int PIPE_TILE = 4096;              // complex elements per tile
@@ -116,12 +121,17 @@ __device__ __forceinline__ cd cmulc(const cd a, const double c, const double d) 
 // stored, N/2 + 1 per transform (fft_auto.h:89-97) - the reference's promote-then-c2c reading of fft_plan_r2c_1d without
 // the promotion and extraction passes. REAL = PIPE_C2R (inverse only): the tile holds N/2 + 1 bins per transform, the
 // Hermitian half X[N - i] = conj(X[i]) is rebuilt while gathering and the real parts are stored (fft_auto.h:99-107).
-enum { PIPE_C2C = 0, PIPE_R2C = 1, PIPE_C2R = 2 };
+// REAL = PIPE_BLUE_FWD / PIPE_BLUE_INV: the two transforms of Bluestein's algorithm for padded lengths N = 512 .. 4096 with the
+// elementwise steps riding on them: FWD reads the caller's n-point rows, multiplies by conj(chirp) and zero-pads while gathering,
+// and multiplies the spectrum by FB before storing it; INV (inverse c2c, 1/N) multiplies by conj(chirp) * y_scale and stores the
+// first n values of every row to the caller's array. Two launches and HBM round trips instead of five, the same arithmetic.
+enum { PIPE_C2C = 0, PIPE_R2C = 1, PIPE_C2R = 2, PIPE_BLUE_FWD = 3, PIPE_BLUE_INV = 4 };
 
 template <int LOGN, bool INV, int REAL = PIPE_C2C>
 __global__ void __launch_bounds__(2 * PIPE_GROUP, 1) fft_pipe_kernel(const PipeArgs a) {
     static_assert(LOGN >= 9 && LOGN <= 12, "one transform must be 512 .. 4096 points");
-    static_assert(REAL == PIPE_C2C || (REAL == PIPE_R2C && !INV) || (REAL == PIPE_C2R && INV), "r2c is forward, c2r inverse");
+    static_assert(REAL == PIPE_C2C || ((REAL == PIPE_R2C || REAL == PIPE_BLUE_FWD) && !INV) || ((REAL == PIPE_C2R || REAL == PIPE_BLUE_INV) && INV),
+                  "r2c and Bluestein's first transform are forward, c2r and its second inverse");
     constexpr int NH = (1 << LOGN) / 2 + 1;   // bins per transform of a half spectrum
     constexpr int N = 1 << LOGN, NT = PIPE_TILE / N;  // transforms per tile
     constexpr int LR0 = LOGN - 8, R0 = 1 << LR0, NB0 = 16 / R0;
@@ -146,7 +156,8 @@ __global__ void __launch_bounds__(2 * PIPE_GROUP, 1) fft_pipe_kernel(const PipeA
         const long long tile = first + (long long)k * stride;
         long long nvalid = a.batch - tile * NT;
         if (nvalid > NT) nvalid = NT;
-        const uint32_t per = REAL == PIPE_R2C ? N * (uint32_t)sizeof(double) : REAL == PIPE_C2R ? NH * (uint32_t)sizeof(cd) : N * (uint32_t)sizeof(cd);
+        const uint32_t per = REAL == PIPE_R2C ? N * (uint32_t)sizeof(double) : REAL == PIPE_C2R ? NH * (uint32_t)sizeof(cd)
+                           : REAL == PIPE_BLUE_FWD ? (uint32_t)a.n_user * (uint32_t)sizeof(cd) : N * (uint32_t)sizeof(cd);
         const uint32_t bytes = (uint32_t)nvalid * per;
         uint64_t* const bar = &full[b + PIPE_STAGES * (rnd & 1)];
         mbar_expect_tx(bar, bytes);
@@ -204,13 +215,21 @@ __global__ void __launch_bounds__(2 * PIPE_GROUP, 1) fft_pipe_kernel(const PipeA
                 const bool up = i > N / 2;
                 y = sm[jj * NH + (up ? N - i : i)];
                 if (!up) y.y = -y.y;
+            } else if constexpr (REAL == PIPE_BLUE_FWD) {
+                // a = x * conj(chirp), zero-padded from n to N (bluestein.c:107-109)
+                const int idx = t + 256 * e, jj = idx >> LOGN, i = idx & (N - 1);
+                y = make_double2(0.0, 0.0);
+                if (i < a.n_user) {
+                    const cd xv = sm[jj * a.n_user + i], w = __ldg(a.chirp + i);
+                    y = make_double2(fma(xv.x, w.x, xv.y * w.y), fma(xv.y, w.x, -(xv.x * w.y)));
+                }
             } else {
                 y = sm[t + 256 * e];
                 if (INV) y.y = -y.y;
             }
             x[(e / R0) * R0 + bitrev_c<LR0>(e % R0)] = y;
         }
-        if constexpr (REAL != PIPE_C2C) group_sync(g);   // the complex tile overwrites other threads' packed inputs: gather everything first
+        if constexpr (REAL == PIPE_R2C || REAL == PIPE_C2R || REAL == PIPE_BLUE_FWD) group_sync(g);   // the complex tile overwrites other threads' packed inputs: gather everything first
 #pragma unroll
         for (int bb = 0; bb < NB0; bb++) SubStageExact<LR0, 1, 0, 0>::run(&x[bb * R0]);
         __syncwarp();  // the swizzle moves a thread's slots within its warp's 32-element rows
@@ -265,6 +284,44 @@ __global__ void __launch_bounds__(2 * PIPE_GROUP, 1) fft_pipe_kernel(const PipeA
                 if (valid) {
 #pragma unroll
                     for (int q = 0; q < 16; q++) p[q << LN16] = x[q].x * sc;
+                }
+            } else if constexpr (REAL == PIPE_BLUE_FWD) {
+                // A * FB (bluestein.c:124-131); factors fetched four at a time ahead of the stores they feed
+                cd* p = a.out + tile * PIPE_TILE + wr1;
+                if (valid) {
+#pragma unroll
+                    for (int q0 = 0; q0 < 16; q0 += 4) {
+                        cd w[4];
+#pragma unroll
+                        for (int i = 0; i < 4; i++) w[i] = __ldg(a.fb + v + ((q0 + i) << LN16));
+#pragma unroll
+                        for (int i = 0; i < 4; i++) {
+                            const cd r = x[q0 + i];
+                            p[(q0 + i) << LN16] = make_double2(fma(r.x, w[i].x, -(r.y * w[i].y)), fma(r.x, w[i].y, r.y * w[i].x));
+                        }
+                    }
+                }
+            } else if constexpr (REAL == PIPE_BLUE_INV) {
+                // y = a * conj(chirp) * y_scale for the first n values of the row (bluestein.c:139-148)
+                cd* p = a.out + (size_t)(tile * NT + j) * a.n_user + v;
+                const double s2 = a.y_scale;
+                if (valid) {
+#pragma unroll
+                    for (int q0 = 0; q0 < 16; q0 += 4) {
+                        cd w[4];
+#pragma unroll
+                        for (int i = 0; i < 4; i++) {
+                            const int idx = v + ((q0 + i) << LN16);
+                            w[i] = idx < a.n_user ? __ldg(a.chirp + idx) : make_double2(0.0, 0.0);
+                        }
+#pragma unroll
+                        for (int i = 0; i < 4; i++) {
+                            cd r = x[q0 + i];
+                            r.x *= sc; r.y *= -sc;
+                            if (v + ((q0 + i) << LN16) < a.n_user)
+                                p[(q0 + i) << LN16] = make_double2(fma(r.x, w[i].x, r.y * w[i].y) * s2, fma(r.y, w[i].x, -(r.x * w[i].y)) * s2);
+                        }
+                    }
                 }
             } else {
                 cd* p = a.out + tile * PIPE_TILE + wr1;

@@ -261,6 +261,7 @@ struct fftb200_plan {
     double scale = 0.0;        // 1/m, or the caller's value for partial plans of a distributed transform
     cd* work = nullptr;        // Bluestein / R2C: padded complex work array, m * batch
     bool fused_c2r = false;    // C2R of 2^14 .. 2^20 points: the fused kernel stores the real parts itself
+    bool pipe_blue = false;    // Bluestein with m = 512 .. 4096: both transforms in the pipe kernel's Bluestein variants, no elementwise kernels
     bool pipe_real = false;    // R2C / C2R of 512 .. 4096 points: the pipe kernel reads reals / half spectra itself (no work array)
     cd* chirp = nullptr;       // Bluestein: n entries
     cd* fb = nullptr;          // Bluestein: FFT_m of the wrapped chirp
@@ -840,6 +841,15 @@ extern "C" int fftb200_plan_create(fftb200_plan** out, const fftb200_plan_desc* 
             if (rc == 0 && cudaStreamSynchronize(p->stream) != cudaSuccess) rc = fail("Bluestein kernel spectrum failed: %s", cudaGetErrorString(cudaGetLastError()));
             if (rc != 0) break;
             p->launches = 2 * (int)p->passes.size() + (can_fuse_pre(p) ? 0 : 1) + (can_fuse_post(p) ? 0 : 2);
+            if (p->passes.size() == 1 && !p->passes[0].k && !p->passes[0].fused_lm && p->passes[0].log_p <= 12 && !getenv("FFTB200_NO_PIPE_BLUE")) {
+                bool ok = true;
+                for (int kind = PIPE_BLUE_FWD; kind <= PIPE_BLUE_INV; kind++)
+                    ok = ok && cudaFuncSetAttribute(pipe_real_func(p->passes[0].log_p, kind), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PIPE_SMEM) == cudaSuccess;
+                if (!ok) { rc = fail("cudaFuncSetAttribute failed"); break; }
+                p->pipe_blue = true;
+                p->launches = 2;
+                p->desc += " [chirp and spectrum factors inside the two transforms]";
+            }
         }
     } while (0);
     if (rc != 0) { fftb200_plan_destroy(p); return -1; }
@@ -1081,6 +1091,21 @@ static int exec_range(fftb200_plan* p, const void* d_in, void* d_out, long long 
     // y = a * conj(chirp) (and 1/n for the inverse direction).
     // Multi-pass plans (m >= 2^21) carry the three elementwise steps on their first / last tile pass: 6 launches and HBM
     // round trips per execution instead of 9 (n = 1000003, same box: x1 0.120 -> 0.109 ms, x16 1.68 -> 1.28 ms, x64 5.81 -> 4.83 ms).
+    if (p->pipe_blue) {
+        if (nbatch <= 0) return 0;
+        const Pass& ps = p->passes[0];
+        const long long ntiles = pass_tiles(ps, nbatch);
+        const int grid = (int)(ntiles < ps.grid_max ? ntiles : ps.grid_max);
+        PipeArgs pa;
+        pa.tab = p->acc; pa.ntiles = ntiles; pa.batch = nbatch;
+        pa.chirp = p->chirp; pa.fb = p->fb; pa.n_user = p->n; pa.y_scale = inverse ? 1.0 / (double)p->n : 1.0;
+        pa.in = (const cd*)d_in; pa.out = p->work; pa.inverse = 0; pa.scale = 1.0;
+        launch_pipe_real(ps.log_p, PIPE_BLUE_FWD, pa, grid, p->stream);
+        pa.in = p->work; pa.out = (cd*)d_out; pa.inverse = 1; pa.scale = p->scale;
+        launch_pipe_real(ps.log_p, PIPE_BLUE_INV, pa, grid, p->stream);
+        CU(cudaGetLastError());
+        return 0;
+    }
     const bool fpre = can_fuse_pre(p), fpost = can_fuse_post(p);
     const double yscale = inverse ? 1.0 / (double)p->n : 1.0;
     FuseSpec pre, fb, post;

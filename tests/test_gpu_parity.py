@@ -75,6 +75,24 @@ def test_bluestein_parity(gpu, port, O, n, direction):
     assert O.rel_l2(y, want) <= TOL
 
 
+@pytest.mark.parametrize("n,batch", [(257, 1), (300, 1000), (1009, 67), (2003, 5), (2048 - 1, 300), (1500, 3)])
+@pytest.mark.parametrize("direction", [-1, 1])
+def test_bluestein_inside_the_pipe_kernel_is_bit_identical(gpu, port, O, n, batch, direction, monkeypatch):
+    """Bluestein with padded length m = 512 .. 4096: chirp multiply + zero padding ride on the first gather of the forward
+    transform, the spectral product on its stores, the final chirp multiply on the stores of the inverse (fft_pipe.cuh,
+    PIPE_BLUE_FWD / INV): 2 launches instead of 5. FFTB200_NO_PIPE_BLUE=1 is the five-kernel path: same arithmetic, identical
+    bits; first and last rows against the oracle; in place."""
+    x = port.fill(56, 0, n * batch).reshape(batch, n)
+    a = gpu.gpu_fft_batch(x, direction)
+    monkeypatch.setenv("FFTB200_NO_PIPE_BLUE", "1")
+    b = gpu.gpu_fft_batch(x, direction)
+    monkeypatch.delenv("FFTB200_NO_PIPE_BLUE")
+    assert np.array_equal(a, b)
+    assert np.array_equal(gpu.gpu_fft_batch(x, direction, inplace=True), a)
+    rows = sorted({0, batch - 1})
+    assert O.rel_l2(a[rows], np.stack([port.fft(x[r], direction) for r in rows])) <= TOL
+
+
 @pytest.mark.parametrize("direction", [-1, 1])
 def test_bluestein_fused_chirp_is_bit_identical(gpu, port, direction, monkeypatch):
     """Multi-pass Bluestein plans (m >= 2^21) apply the chirp factors and the spectral product inside the first / last
