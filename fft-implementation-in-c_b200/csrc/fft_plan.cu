@@ -672,7 +672,9 @@ static int enqueue_c2c(fftb200_plan* p, const cd* in, cd* out, int inverse, long
         }
         const cd* src = ps.src == BUF_IN ? in : ps.src == BUF_OUT ? out : p->scratch;
         cd* dst = ps.dst == BUF_OUT ? out : p->scratch;
-        if (ps.lastpipe && !post && !p->peers) {
+        // (from 8 transforms per execution: below that the late-stage twiddles come from HBM for most tiles and the tile kernel's
+        // two CTAs per SM hide that better - 2^24: x1 0.323 / 0.308 ms, x4 1.151 / 1.086 ms, x16 4.18 / 4.32 ms ring / tile)
+        if (ps.lastpipe && nbatch >= 8 && !post && !p->peers) {
             LastPipeArgs la;
             la.in = src; la.out = dst; la.tab = p->tab;
             la.batch = nbatch; la.log_n = p->log_n; la.log_m = ps.log_m;

@@ -367,10 +367,11 @@ def test_small_host_transforms_zero_copy_equals_staged(gpu, port, O, n, monkeypa
     assert O.rel_l2(a[0], port.fft(x, -1)) <= TOL
 
 
-@pytest.mark.parametrize("log_n,batch", [(22, 3), (23, 2), (24, 1)])
+@pytest.mark.parametrize("log_n,batch", [(22, 11), (23, 9), (24, 8)])
 @pytest.mark.parametrize("direction", [-1, 1])
 def test_tma_ring_last_pass_equals_tile_last_pass(gpu, port, O, log_n, batch, direction, monkeypatch):
-    """N = 2^22 .. 2^24: the last pass runs in fft_lastpipe_kernel (TMA ring, the fused kernel's pass-B dataflow);
+    """N = 2^22 .. 2^24, 8 or more transforms per execution: the last pass runs in fft_lastpipe_kernel (TMA ring, the fused
+    kernel's pass-B dataflow);
     FFTB200_NO_LASTPIPE=1 keeps fft_tile_kernel<LAST>. Same table twiddles and butterflies: bit-identical where the radix
     split is the same (2^23, 2^24), within 1e-15 otherwise; last transform against the oracle."""
     n = 1 << log_n
