@@ -29,7 +29,8 @@
 //
 // Measured alternatives (same box A/B, N = 4096 x 65536, ms): this form 1.31-1.32; all 8 last-pass twiddles
 // in registers 1.51 (spills on the loop-carried path); the 4 powers in a per-thread shared table 1.43 (the
-// LSU / MIO queue is the most loaded pipe: every extra LDS costs more than 16 extra DFMA).
+// LSU / MIO queue is the most loaded pipe: every extra LDS costs more than 16 extra DFMA). For N <= 2048 the four powers are
+// re-read per tile from global memory (L1 hits) instead: these sizes are not HBM-bound and the freed registers are worth 8-9 %.
 #pragma once
 #include "fft_tile.cuh"
 
@@ -189,8 +190,15 @@ __global__ void __launch_bounds__(2 * PIPE_GROUP, 1) fft_pipe_kernel(const PipeA
     // last sub-pass: stage (LN16 + s), position kappa = v -> tab[(h << LN16) + v - 1]. The four powers
     // w^8, w^4, w^2, w (h = 1, 2, 4, 8) stay in registers; h = 5, 9, 10, 11 are w^2 * W8, w * W16, w * W8,
     // w * W16^3, rebuilt per tile (16 FP64 instructions) to keep the register file free of spills.
-    const cd wa = __ldg(a.tab + (v - 1) + (1 << LN16)), wb = __ldg(a.tab + (v - 1) + (2 << LN16));
-    const cd wc = __ldg(a.tab + (v - 1) + (4 << LN16)), wd = __ldg(a.tab + (v - 1) + (8 << LN16));
+    // N = 4096 keeps them in registers for the whole kernel (HBM-bound, 1.31 vs 1.36 ms); the smaller sizes are bound by the
+    // butterflies and exchanges and gain from the eight registers: they re-read the four entries per tile (L1 hits):
+    // same box, 2^28 points: N = 512 1.41 -> 1.35, N = 1024 1.46 -> 1.33, N = 2048 1.42 -> 1.30 ms
+    constexpr bool TW_REGS = LOGN == 12 && REAL == PIPE_C2C;   // (the real / Bluestein variants of N = 4096 are not HBM-bound either)
+    cd wa0, wb0, wc0, wd0;
+    if constexpr (TW_REGS) {
+        wa0 = __ldg(a.tab + (v - 1) + (1 << LN16)); wb0 = __ldg(a.tab + (v - 1) + (2 << LN16));
+        wc0 = __ldg(a.tab + (v - 1) + (4 << LN16)); wd0 = __ldg(a.tab + (v - 1) + (8 << LN16));
+    }
     const int rd1 = j * N + cp + 256 * kloc1;   // sub-pass 1 gather base
     const int wr1 = j * N + v;                  // sub-pass 1 scatter base
     const int rd2 = j * N + 16 * v;             // sub-pass 2 gather base
@@ -253,6 +261,13 @@ __global__ void __launch_bounds__(2 * PIPE_GROUP, 1) fft_pipe_kernel(const PipeA
         // ---- sub-pass 2: radix 16, M = N/16, S = 1 ----
 #pragma unroll
         for (int rho = 0; rho < 16; rho++) x[bitrev_c<4>(rho)] = sm[pipe_swz(rd2 + rho)];
+        cd wa, wb, wc, wd;
+        if constexpr (TW_REGS) {
+            wa = wa0; wb = wb0; wc = wc0; wd = wd0;
+        } else {
+            wa = __ldg(a.tab + (v - 1) + (1 << LN16)); wb = __ldg(a.tab + (v - 1) + (2 << LN16));
+            wc = __ldg(a.tab + (v - 1) + (4 << LN16)); wd = __ldg(a.tab + (v - 1) + (8 << LN16));
+        }
         group_sync(g);  // the buffer is free: refill it with this CTA's tile k + 3
         if (t == 0 && k + PIPE_STAGES < my_tiles) {
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");

@@ -54,6 +54,10 @@ struct Stage13 {
     }
 };
 
+#ifndef PIPE13_BULK
+#define PIPE13_BULK 1
+#endif
+
 template <bool INV>
 __global__ void __launch_bounds__(2 * PIPE_GROUP, 1) fft_pipe13_kernel(const PipeArgs a, const __grid_constant__ CUtensorMap tm_in) {
     constexpr int N = 8192, H = 4096;
@@ -77,8 +81,12 @@ __global__ void __launch_bounds__(2 * PIPE_GROUP, 1) fft_pipe13_kernel(const Pip
         cd* dst = bufs + (size_t)b * PIPE_TILE;
         uint64_t pol;
         asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(pol));
+#if PIPE13_BULK
+        bulk_load(dst, a.in + tr * N + (h & 1) * H, H * (uint32_t)sizeof(cd), bar);   // half h = elements [4096 (h & 1), + 4096)
+#else
 #pragma unroll 1
         for (int i = 0; i < 16; i++) tma_load_4d(dst + 256 * i, &tm_in, 0, h & 1, 256 * i, (int)tr, bar, pol);
+#endif
     };
 
     if (threadIdx.x == 0) {
@@ -98,8 +106,6 @@ __global__ void __launch_bounds__(2 * PIPE_GROUP, 1) fft_pipe13_kernel(const Pip
     }
 
     const int cp = t & 15, kloc1 = t >> 4;
-    const cd wa = __ldg(a.tab + (t - 1) + (1 << LN16)), wb = __ldg(a.tab + (t - 1) + (2 << LN16));
-    const cd wc = __ldg(a.tab + (t - 1) + (4 << LN16)), wd = __ldg(a.tab + (t - 1) + (8 << LN16));
     const int rd1 = cp + 256 * kloc1;
     const cd* const tw1p = tw1s + kloc1 * 8;
     const double sc = a.scale;
@@ -111,6 +117,28 @@ __global__ void __launch_bounds__(2 * PIPE_GROUP, 1) fft_pipe13_kernel(const Pip
         mbar_wait_bounded(&full[b + PIPE_STAGES * (round & 1)], (round >> 1) & 1);   // a lost load traps instead of hanging the GPU
         cd x[16];
         // ---- sub-pass 0: radix 16, exact constants, in place ----
+#if PIPE13_BULK
+        {
+            // the halves arrive as they lie in memory (x[0 .. 4095] and x[4096 .. 8191], full-rate bulk copies); group g takes
+            // the samples x[g + 2 t] out of BOTH: 16-byte reads at a 32-byte stride (two wavefronts per quarter warp instead of
+            // one) - cheaper than letting the TMA write 4096 16-byte rows per half into shared memory
+            const int bp = g == 0 ? (b + 1 == PIPE_STAGES ? 0 : b + 1) : (b == 0 ? PIPE_STAGES - 1 : b - 1);
+            const uint32_t rp = g == 0 ? round + (b + 1 == PIPE_STAGES ? 1 : 0) : round - (b == 0 ? 1 : 0);
+            mbar_wait_bounded(&full[bp + PIPE_STAGES * (rp & 1)], (rp >> 1) & 1);
+            const cd* const other = bufs + (size_t)bp * PIPE_TILE;
+            const cd* const lo = g == 0 ? sm : other;
+            const cd* const hi = g == 0 ? other : sm;
+#pragma unroll
+            for (int i = 0; i < 16; i++) {
+                const int e = bitrev_c<4>(i);
+                cd y = (e < 8 ? lo : hi)[g + 2 * (t + 256 * (e & 7))];
+                if (INV) y.y = -y.y;
+                x[i] = y;
+            }
+        }
+        SubStageExact<4, 1, 0, 0>::run(x);
+        bar_sync_n(6, 2 * PIPE_GROUP);   // both groups have read both halves: each scatters into its own buffer
+#else
 #pragma unroll
         for (int i = 0; i < 16; i++) {   // in the order the butterflies consume them: the first pairs arrive first
             cd y = sm[t + 256 * bitrev_c<4>(i)];
@@ -119,6 +147,7 @@ __global__ void __launch_bounds__(2 * PIPE_GROUP, 1) fft_pipe13_kernel(const Pip
         }
         SubStageExact<4, 1, 0, 0>::run(x);
         __syncwarp();
+#endif
 #pragma unroll
         for (int e = 0; e < 16; e++) sm[pipe_swz(t + 256 * e)] = x[e];
         group_sync(g);
@@ -138,6 +167,10 @@ __global__ void __launch_bounds__(2 * PIPE_GROUP, 1) fft_pipe13_kernel(const Pip
         // ---- sub-pass 2: radix 16 after 8 stages ----
 #pragma unroll
         for (int i = 0; i < 16; i++) x[i] = sm[pipe_swz(16 * t + bitrev_c<4>(i))];
+        // the four last-sub-pass twiddle powers are re-read per half (L1 hits) instead of living in registers for the whole
+        // kernel: no spills on the loop-carried path (same box: 1.874 -> 1.772 ms)
+        const cd wa = __ldg(a.tab + (t - 1) + (1 << LN16)), wb = __ldg(a.tab + (t - 1) + (2 << LN16));
+        const cd wc = __ldg(a.tab + (t - 1) + (4 << LN16)), wd = __ldg(a.tab + (t - 1) + (8 << LN16));
         group_sync(g);
         // group 0's buffer is free now: refill it with half h + 3 (the odd half of the next transform). Group 1's buffer
         // hosts the stage-13 trade first: tell group 0 that every gather from it is done.
