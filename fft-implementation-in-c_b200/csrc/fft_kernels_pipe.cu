@@ -49,13 +49,13 @@ void launch_pipe(int logn, const PipeArgs& a, int grid, cudaStream_t s) {
     }
 }
 
-// N = 8192: two 4096-point halves per transform, de-interleaved by the TMA (fft_pipe13.cuh)
+// N = 8192: two 4096-point halves per transform (fft_pipe13.cuh)
 const void* pipe13_func(int inverse) {
     return inverse ? (const void*)fft_pipe13_kernel<true> : (const void*)fft_pipe13_kernel<false>;
 }
-cudaError_t launch_pipe13(const PipeArgs& a, const CUtensorMap& tm, int grid, cudaStream_t s) {
-    if (a.inverse) fft_pipe13_kernel<true><<<grid, 2 * PIPE_GROUP, PIPE_SMEM, s>>>(a, tm);
-    else fft_pipe13_kernel<false><<<grid, 2 * PIPE_GROUP, PIPE_SMEM, s>>>(a, tm);
+cudaError_t launch_pipe13(const PipeArgs& a, int grid, cudaStream_t s) {
+    if (a.inverse) fft_pipe13_kernel<true><<<grid, 2 * PIPE_GROUP, PIPE_SMEM, s>>>(a);
+    else fft_pipe13_kernel<false><<<grid, 2 * PIPE_GROUP, PIPE_SMEM, s>>>(a);
     return cudaGetLastError();
 }
 }  // namespace fftb200

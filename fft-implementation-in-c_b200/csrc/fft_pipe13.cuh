@@ -6,19 +6,22 @@
 //
 // Decomposition N = 4096 * 2 in the reference's DIT order: stages 1 .. 12 are two independent 4096-point transforms
 // of the even and the odd samples x[c + 2 t] (c = 0, 1), stage 13 combines X[k], X[k + 4096] = Y0[k] +- w^k Y1[k].
-//   * the de-interleave is done by the TMA: the input is described as a [transform][t][c][re, im] tensor and a "half"
-//     (one c of one transform, 64 KB) arrives as 16 boxes of 256 rows of 16 bytes. Strided 16-byte rows cost the TMA
-//     one row per clock (tools/clbench.cu: 4.0 TB/s chip-wide), which is above what the HBM roofline asks for reads
-//     (3.3 TB/s), and the LSU - the most loaded pipe of fft_pipe_kernel - sees none of it;
-//   * group c (256 threads) runs the unchanged 4096-point dataflow of fft_pipe_kernel<12> on half c: the halves
-//     h = 2 k + c of this CTA's transforms k go through the same three-buffer ring with the same two-barriers-per-
-//     buffer scheme (tile index = h);
+//   * the two halves of a transform arrive as they lie in memory (x[0 .. 4095], x[4096 .. 8191]: full-rate bulk copies into
+//     two ring buffers) and group c takes its samples x[c + 2 t] out of BOTH while gathering its first sub-pass: 16-byte
+//     reads at a 32-byte stride (two shared-memory wavefronts per quarter warp instead of one). Letting the TMA do the
+//     de-interleave (a [transform][t][c] tensor, 16 boxes of 256 rows of 16 bytes per half) was measured first: it keeps the
+//     LSU out of it but writes 4096 16-byte rows per half into shared memory and doubles the L2 -> SM traffic: 1.92 vs
+//     1.87 ms, and far less stable;
+//   * after that first gather (and one CTA-wide barrier: both groups have read both buffers) group c runs the unchanged
+//     4096-point dataflow of fft_pipe_kernel<12> in its own buffer: the halves h = 2 k + c of this CTA's transforms k go
+//     through the same three-buffer ring with the same two-barriers-per-buffer scheme (tile index = h; both groups wait
+//     for every fill);
 //   * stage 13: each thread holds Y_c[t + 256 q], q < 16. Group 0 does the butterflies q < 8, group 1 q >= 8: the
 //     halves trade 8 values per thread through group 1's buffer (32 KB each way), and since
 //     w13[k + 2048] = -i w13[k] both groups use w13[t + 256 e] = w13[t] * W32^e (one table entry per thread, re-read from
 //     L1 per transform to keep the register file free of spills). Group 0's buffer is not involved, so it is refilled
-//     as early as in fft_pipe_kernel (after the last gather): that load - the odd half of the NEXT transform - is the one on the critical path, the even half of
-//     the transform after it goes into group 1's buffer after the trade;
+//     as early as in fft_pipe_kernel (after the last gather): that load - the second half of the NEXT transform - is the
+//     one on the critical path, the first half of the transform after it goes into group 1's buffer after the trade;
 //   * results leave from registers, X[k] and X[k + 4096], 512 contiguous bytes per warp instruction.
 // Twiddles are the accurate tables for all 13 stages (SURVEY.md 7.0 hybrid rule; 8192-point mismatch vs the
 // reference recurrence 2.6e-14, checked by the GPU parity tests at 1e-12).
@@ -54,12 +57,8 @@ struct Stage13 {
     }
 };
 
-#ifndef PIPE13_BULK
-#define PIPE13_BULK 1
-#endif
-
 template <bool INV>
-__global__ void __launch_bounds__(2 * PIPE_GROUP, 1) fft_pipe13_kernel(const PipeArgs a, const __grid_constant__ CUtensorMap tm_in) {
+__global__ void __launch_bounds__(2 * PIPE_GROUP, 1) fft_pipe13_kernel(const PipeArgs a) {
     constexpr int N = 8192, H = 4096;
     constexpr int LN16 = 8;
 
@@ -73,20 +72,12 @@ __global__ void __launch_bounds__(2 * PIPE_GROUP, 1) fft_pipe13_kernel(const Pip
     const int my_tr = first < a.ntiles ? (int)((a.ntiles - first + stride - 1) / stride) : 0;   // transforms of this CTA
     const int my_halves = 2 * my_tr;
 
-    // half h = 2 k + c of this CTA's k-th transform -> buffer b (= h % 3), 16 boxes of 256 rows x 16 bytes
+    // half h = 2 k + (h & 1) of this CTA's k-th transform = elements [4096 (h & 1), + 4096) -> buffer b (= h % 3)
     auto issue = [&](int h, int b, uint32_t rnd) {
         const long long tr = first + (long long)(h >> 1) * stride;
         uint64_t* const bar = &full[b + PIPE_STAGES * (rnd & 1)];
         mbar_expect_tx(bar, H * (uint32_t)sizeof(cd));
-        cd* dst = bufs + (size_t)b * PIPE_TILE;
-        uint64_t pol;
-        asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(pol));
-#if PIPE13_BULK
-        bulk_load(dst, a.in + tr * N + (h & 1) * H, H * (uint32_t)sizeof(cd), bar);   // half h = elements [4096 (h & 1), + 4096)
-#else
-#pragma unroll 1
-        for (int i = 0; i < 16; i++) tma_load_4d(dst + 256 * i, &tm_in, 0, h & 1, 256 * i, (int)tr, bar, pol);
-#endif
+        bulk_load(bufs + (size_t)b * PIPE_TILE, a.in + tr * N + (h & 1) * H, H * (uint32_t)sizeof(cd), bar);
     };
 
     if (threadIdx.x == 0) {
@@ -117,7 +108,6 @@ __global__ void __launch_bounds__(2 * PIPE_GROUP, 1) fft_pipe13_kernel(const Pip
         mbar_wait_bounded(&full[b + PIPE_STAGES * (round & 1)], (round >> 1) & 1);   // a lost load traps instead of hanging the GPU
         cd x[16];
         // ---- sub-pass 0: radix 16, exact constants, in place ----
-#if PIPE13_BULK
         {
             // the halves arrive as they lie in memory (x[0 .. 4095] and x[4096 .. 8191], full-rate bulk copies); group g takes
             // the samples x[g + 2 t] out of BOTH: 16-byte reads at a 32-byte stride (two wavefronts per quarter warp instead of
@@ -138,16 +128,6 @@ __global__ void __launch_bounds__(2 * PIPE_GROUP, 1) fft_pipe13_kernel(const Pip
         }
         SubStageExact<4, 1, 0, 0>::run(x);
         bar_sync_n(6, 2 * PIPE_GROUP);   // both groups have read both halves: each scatters into its own buffer
-#else
-#pragma unroll
-        for (int i = 0; i < 16; i++) {   // in the order the butterflies consume them: the first pairs arrive first
-            cd y = sm[t + 256 * bitrev_c<4>(i)];
-            if (INV) y.y = -y.y;
-            x[i] = y;
-        }
-        SubStageExact<4, 1, 0, 0>::run(x);
-        __syncwarp();
-#endif
 #pragma unroll
         for (int e = 0; e < 16; e++) sm[pipe_swz(t + 256 * e)] = x[e];
         group_sync(g);
@@ -232,6 +212,6 @@ __global__ void __launch_bounds__(2 * PIPE_GROUP, 1) fft_pipe13_kernel(const Pip
 }
 
 const void* pipe13_func(int inverse);
-cudaError_t launch_pipe13(const PipeArgs& a, const CUtensorMap& tm, int grid, cudaStream_t s);
+cudaError_t launch_pipe13(const PipeArgs& a, int grid, cudaStream_t s);
 
 }  // namespace fftb200

@@ -333,7 +333,7 @@ static int build_passes(fftb200_plan* p, DeviceState* ds) {
         return 0;
     }
     if (L == 13 && p->acc && !getenv("FFTB200_NO_PIPE13") && !getenv("FFTB200_NO_PIPE")) {
-        // one visit to shared memory: two TMA-de-interleaved 4096-point halves + stage 13 (fft_pipe13.cuh)
+        // one visit to shared memory: two 4096-point halves + stage 13 (fft_pipe13.cuh)
         Pass ps;
         ps.k = nullptr; ps.log_p = 13; ps.log_m = 0;
         ps.nt = 1; ps.shift = 0;
@@ -342,7 +342,7 @@ static int build_passes(fftb200_plan* p, DeviceState* ds) {
             CU(cudaFuncSetAttribute(pipe13_func(iv), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PIPE_SMEM));
         ps.grid_max = ds->sms;
         p->passes.push_back(ps);
-        p->desc += "P13(tma de-interleave, ring 3 x 64KB halves, 2x256 thr, stage 13 traded through shared memory)";
+        p->desc += "P13(tma ring 3 x 64KB halves, 2x256 thr, de-interleave on the first gather, stage 13 traded through shared memory)";
         return 0;
     }
     if (L >= 13 && L <= 20 && p->acc && !getenv("FFTB200_NO_FUSED")) {
@@ -648,23 +648,7 @@ static int enqueue_c2c(fftb200_plan* p, const cd* in, cd* out, int inverse, long
             pa.ntiles = ntiles; pa.batch = nbatch;
             pa.inverse = inverse; pa.scale = p->scale;
             if (ps.log_p == 13) {
-                // the input as [transform][t][c][re, im]: a box is 256 values of t for one c (rows of 16 bytes at stride 32)
-                EncodeTiledFn enc = encode_tiled_fn();
-                if (!enc) return fail("cuTensorMapEncodeTiled is not available from this driver");
-                CUtensorMap tm;
-                const cuuint64_t gdim[4] = {2, 2, 4096, (cuuint64_t)nbatch};
-                const cuuint64_t gstr[3] = {sizeof(cd), 2 * sizeof(cd), 8192 * sizeof(cd)};
-                const cuuint32_t box[4] = {2, 1, 256, 1};
-                const cuuint32_t estr[4] = {1, 1, 1, 1};
-                int promo = 1;
-                if (const char* e = getenv("FFTB200_P13_PROMO")) promo = atoi(e);
-                const CUresult r = enc(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 4, (void*)in, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                                       CU_TENSOR_MAP_SWIZZLE_NONE,
-                                       promo >= 2 ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B : promo == 1 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B
-                                                                                                     : CU_TENSOR_MAP_L2_PROMOTION_NONE,
-                                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-                if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled failed (%d) for the 8192-point input", (int)r);
-                CU(launch_pipe13(pa, tm, grid, p->stream));
+                CU(launch_pipe13(pa, grid, p->stream));
                 continue;
             }
             launch_pipe(ps.log_p, pa, grid, p->stream);

@@ -300,8 +300,8 @@ def test_fused_two_pass_many_groups(gpu, port, O, log_n, batch):
 
 @pytest.mark.parametrize("batch", [1, 2, 3, 147, 149, 445, 5000])
 def test_pipe13_one_visit_kernel(gpu, port, O, batch):
-    """N = 8192 runs in fft_pipe13_kernel (csrc/fft_pipe13.cuh): two TMA-de-interleaved 4096-point halves per transform in
-    a three-buffer ring, stage 13 traded between the two thread groups. Batches below, at and ragged against the grid
+    """N = 8192 runs in fft_pipe13_kernel (csrc/fft_pipe13.cuh): the two 4096-point halves of a transform in a three-buffer
+    ring, de-interleaved on the first gather, stage 13 traded between the two thread groups. Batches below, at and ragged against the grid
     (148 CTAs), so CTAs with 0, 1, 2 and many transforms and every ring phase are exercised; forward against the oracle,
     the same plan twice, then the in-place inverse of everything against the input."""
     import torch
