@@ -7,13 +7,15 @@ namespace fftb200 {
 struct KernelInfo {
     int mode, logp, logc, triv, nt, threads;
     size_t smem;
-    const void* func;
+    const void* func;       // forward instantiation
+    const void* func_inv;   // inverse instantiation (same resources; attributes are set on both)
     void (*launch)(const TileArgs&, int grid, cudaStream_t);
 };
 
 template <class C>
 static void launch_tile(const TileArgs& a, int grid, cudaStream_t s) {
-    fft_tile_kernel<C><<<grid, C::THREADS, C::SMEM_BYTES, s>>>(a);
+    if (a.inverse) fft_tile_kernel<C, true><<<grid, C::THREADS, C::SMEM_BYTES, s>>>(a);
+    else fft_tile_kernel<C, false><<<grid, C::THREADS, C::SMEM_BYTES, s>>>(a);
 }
 
 template <class C>
@@ -21,7 +23,8 @@ static KernelInfo make_info() {
     KernelInfo k;
     k.mode = C::MODE; k.logp = C::LOGP; k.logc = C::LOGC; k.triv = C::TRIV ? 1 : 0; k.nt = C::NT;
     k.threads = C::THREADS; k.smem = C::SMEM_BYTES;
-    k.func = (const void*)fft_tile_kernel<C>;
+    k.func = (const void*)fft_tile_kernel<C, false>;
+    k.func_inv = (const void*)fft_tile_kernel<C, true>;
     k.launch = launch_tile<C>;
     return k;
 }

@@ -383,6 +383,7 @@ static int build_passes(fftb200_plan* p, DeviceState* ds) {
         lz.nt = 0; lz.shift = 16 - lz.k->logc;
         lz.src = BUF_SCRATCH; lz.dst = BUF_OUT; lz.final_pass = 1;
         CU(cudaFuncSetAttribute(lz.k->func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lz.k->smem));
+        CU(cudaFuncSetAttribute(lz.k->func_inv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lz.k->smem));
         int occ = 0;
         CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, lz.k->func, lz.k->threads, lz.k->smem));
         if (occ < 1) return fail("kernel variant does not fit on an SM");
@@ -421,6 +422,7 @@ static int build_passes(fftb200_plan* p, DeviceState* ds) {
         ps.dst = ((np - 1 - i) % 2 == 0) ? BUF_OUT : BUF_SCRATCH;
         ps.final_pass = (i == np - 1);
         CU(cudaFuncSetAttribute(ps.k->func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ps.k->smem));
+        CU(cudaFuncSetAttribute(ps.k->func_inv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ps.k->smem));
         int occ = 0;
         CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ps.k->func, ps.k->threads, ps.k->smem));
         if (occ < 1) return fail("kernel variant does not fit on an SM");
@@ -919,7 +921,8 @@ extern "C" int fftb200_plan_create_partial(fftb200_plan** out, const fftb200_pla
             ps.src = (i == 0) ? BUF_IN : (((np - 1 - (i - 1)) % 2 == 0) ? BUF_OUT : BUF_SCRATCH);
             ps.dst = ((np - 1 - i) % 2 == 0) ? BUF_OUT : BUF_SCRATCH;
             ps.final_pass = (i == np - 1);
-            if (cudaFuncSetAttribute(ps.k->func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ps.k->smem) != cudaSuccess) { rc = fail("cudaFuncSetAttribute failed"); break; }
+            if (cudaFuncSetAttribute(ps.k->func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ps.k->smem) != cudaSuccess ||
+                cudaFuncSetAttribute(ps.k->func_inv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ps.k->smem) != cudaSuccess) { rc = fail("cudaFuncSetAttribute failed"); break; }
             int occ = 0;
             if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ps.k->func, ps.k->threads, ps.k->smem) != cudaSuccess || occ < 1) { rc = fail("kernel variant does not fit on an SM"); break; }
             ps.grid_max = ds->sms * occ;

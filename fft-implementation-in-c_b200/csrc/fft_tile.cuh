@@ -179,7 +179,7 @@ struct TileCtx {
 // ---------------------------------------------------------------------------------------------
 // one sub-pass: gather -> radix-2^LR butterflies -> scatter
 // ---------------------------------------------------------------------------------------------
-template <class C, int I>
+template <class C, int I, bool INV>
 __device__ __forceinline__ void subpass(cd (&v)[C::E], cd* __restrict__ sm, const int t, const TileArgs& a,
                                         const TileCtx& cx) {
     constexpr int LR = C::lr(I), R = 1 << LR, NB = C::E / R;
@@ -214,7 +214,7 @@ __device__ __forceinline__ void subpass(cd (&v)[C::E], cd* __restrict__ sm, cons
 #pragma unroll
                 for (int rho = 0; rho < R; rho++) {
                     cd x = p[rho << (C::LOGP - LR)];
-                    if (a.inverse) x.y = -x.y;
+                    if (INV) x.y = -x.y;
                     v[b * R + bitrev_c<LR>(rho)] = x;
                 }
             } else {
@@ -240,7 +240,7 @@ __device__ __forceinline__ void subpass(cd (&v)[C::E], cd* __restrict__ sm, cons
                     for (int rho = 0; rho < R; rho++) {
                         cd x = make_double2(0.0, 0.0);
                         if (cx.valid) x = p[rho * step];
-                        if (a.inverse) x.y = -x.y;
+                        if (INV) x.y = -x.y;
                         v[b * R + bitrev_c<LR>(rho)] = x;
                     }
                 }
@@ -273,8 +273,8 @@ __device__ __forceinline__ void subpass(cd (&v)[C::E], cd* __restrict__ sm, cons
 
     // ---- scatter ----
     if constexpr (FINAL) {
-        const bool conj_out = a.inverse != 0;
-        const double sc = (a.inverse && a.final_pass) ? a.scale : 1.0;
+        constexpr bool conj_out = INV;
+        const double sc = (INV && a.final_pass) ? a.scale : 1.0;
 #pragma unroll
         for (int b = 0; b < NB; b++) {
             const int u = ub[b];
@@ -330,7 +330,8 @@ __device__ __forceinline__ void subpass(cd (&v)[C::E], cd* __restrict__ sm, cons
 // ---------------------------------------------------------------------------------------------
 // the kernel: persistent loop over tiles
 // ---------------------------------------------------------------------------------------------
-template <class C>
+// INV: conjugate in, conjugate (and scale, on the pass that ends the plan) out - compiled in, not selected per element
+template <class C, bool INV>
 __global__ void __launch_bounds__(C::THREADS, C::MINB) fft_tile_kernel(const TileArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     cd* sm_all = reinterpret_cast<cd*>(smem_raw);
@@ -378,10 +379,10 @@ __global__ void __launch_bounds__(C::THREADS, C::MINB) fft_tile_kernel(const Til
             cx.kap_base = (int)k0; cx.kap_col = 1;
         }
         cd v[C::E];
-        subpass<C, 0>(v, sm, t, a, cx);
-        if constexpr (C::NSUB > 1) subpass<C, 1>(v, sm, t, a, cx);
-        if constexpr (C::NSUB > 2) subpass<C, 2>(v, sm, t, a, cx);
-        if constexpr (C::NSUB > 3) subpass<C, 3>(v, sm, t, a, cx);
+        subpass<C, 0, INV>(v, sm, t, a, cx);
+        if constexpr (C::NSUB > 1) subpass<C, 1, INV>(v, sm, t, a, cx);
+        if constexpr (C::NSUB > 2) subpass<C, 2, INV>(v, sm, t, a, cx);
+        if constexpr (C::NSUB > 3) subpass<C, 3, INV>(v, sm, t, a, cx);
     }
 }
 
