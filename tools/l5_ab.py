@@ -1,0 +1,24 @@
+import ctypes as C, json, os, sys
+sys.path.insert(0, "/root/repo")
+import fftb200_loader
+F = fftb200_loader.load(); L = F.lib
+F.require_gpu()
+n = 1 << 21
+for batch in (4, 8, 16, 32, 64):
+    tot = n * batch
+    m_in = L.fft_gpu_alloc(tot); m_out = L.fft_gpu_alloc(tot)
+    L.fftb200_fill_splitmix(L.fftb200_devptr_of(m_in), 43, 0, tot)
+    res = {}
+    for tag, env in (("default", {}), ("three_pass", {"FFTB200_NO_FUSED_COLS": "1"}), ("cols_L5", {"FFTB200_FORCE_L5": "1"})):
+        for k in ("FFTB200_NO_FUSED_COLS", "FFTB200_FORCE_L5"): os.environ.pop(k, None)
+        os.environ.update(env)
+        plan = L.fft_gpu_plan_1d(n, batch, -1); eng = L.fftb200_engine_of(plan)
+        din, dout = L.fftb200_devptr_of(m_in), L.fftb200_devptr_of(m_out)
+        ts = []; ms = C.c_float()
+        for i in range(15):
+            L.fftb200_timer_start(eng); L.fftb200_plan_exec_async(eng, din, dout); L.fftb200_timer_stop(eng, C.byref(ms))
+            if i >= 3: ts.append(ms.value)
+        res[tag] = round(min(ts), 4); res[tag + "_plan"] = L.fftb200_plan_describe(eng).decode().split(": ")[-1][:24]
+        L.fft_gpu_destroy_plan(plan)
+    print(json.dumps({"batch": batch, **res}), flush=True)
+    L.fft_gpu_free(m_in); L.fft_gpu_free(m_out)
