@@ -370,7 +370,9 @@ static int build_passes(fftb200_plan* p, DeviceState* ds) {
     // x8 0.280 / 0.290, x16 0.524 / 0.556, x64 2.00 / 2.11 ms); inside Bluestein the three-pass plan carries the chirp factor on its first
     // pass and stays ahead up to x16 (1.22 / 1.25 ms), level at x32
     const int l5_from = p->kind == FFTB200_C2C ? 8 : 32;
-    if (L >= ((getenv("FFTB200_NO_L5") || (p->batch < l5_from && !getenv("FFTB200_FORCE_L5"))) ? 22 : 21) && L <= 25 && p->acc && !getenv("FFTB200_NO_FUSED") && !getenv("FFTB200_NO_FUSED_COLS") && !getenv("FFTB200_SPLIT")) {
+    // (a single 2^22-point transform is the one other case where three tile passes win: 0.090 vs 0.095 ms)
+    const bool small22 = L == 22 && p->batch == 1 && !getenv("FFTB200_FORCE_L5");
+    if (L >= ((getenv("FFTB200_NO_L5") || (p->batch < l5_from && !getenv("FFTB200_FORCE_L5"))) ? 22 : 21) && L <= 25 && !small22 && p->acc && !getenv("FFTB200_NO_FUSED") && !getenv("FFTB200_NO_FUSED_COLS") && !getenv("FFTB200_SPLIT")) {
         // stages 1 .. 16 in the fused kernel's column mode (intermediate in L2), then one LAST tile pass: two HBM round trips
         Pass fz;
         fz.k = nullptr; fz.fused_lm = 8; fz.fused_lr = 8; fz.fused_cols = 1;
