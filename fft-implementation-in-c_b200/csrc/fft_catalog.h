@@ -37,8 +37,8 @@ const KernelInfo* kernels_last(int* count);
 // persistent TMA-fed kernels (fft_pipe.cuh), defined in fft_kernels_pipe.cu
 struct PipeArgs;
 const void* pipe_func(int logn, int inverse);                                  // nullptr if no variant
-void launch_pipe(int logn, const PipeArgs& a, int grid, cudaStream_t s);
+cudaError_t launch_pipe(int logn, const PipeArgs& a, int grid, cudaStream_t s);
 const void* pipe_real_func(int logn, int kind);                                // PIPE_R2C / PIPE_C2R variants (fft_pipe.cuh)
-void launch_pipe_real(int logn, int kind, const PipeArgs& a, int grid, cudaStream_t s);
+cudaError_t launch_pipe_real(int logn, int kind, const PipeArgs& a, int grid, cudaStream_t s);
 
 }  // namespace fftb200

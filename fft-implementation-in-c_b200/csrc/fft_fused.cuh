@@ -127,18 +127,6 @@ template <> struct SwzBlast<10> { typedef Swz<4, 10, 11> type; };
 __device__ __forceinline__ void mbar_arrive_cnt(uint64_t* bar, int count) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
 }
-// bounded wait: a protocol error traps (the launch fails with an error) instead of hanging the GPU
-__device__ __forceinline__ void mbar_wait_bounded(uint64_t* bar, uint32_t parity) {
-#pragma unroll 1
-    for (int it = 0; it < (1 << 24); it++) {
-        uint32_t ok;
-        asm volatile(
-            "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
-            : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
-        if (ok) return;
-    }
-    __trap();
-}
 __device__ __forceinline__ int ld_acquire_gpu(const int* p) {
     int v;
     asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");

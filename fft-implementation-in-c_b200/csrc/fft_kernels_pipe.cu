@@ -21,7 +21,7 @@ const void* pipe_real_func(int logn, int kind) {
     }
     return nullptr;
 }
-void launch_pipe_real(int logn, int kind, const PipeArgs& a, int grid, cudaStream_t s) {
+cudaError_t launch_pipe_real(int logn, int kind, const PipeArgs& a, int grid, cudaStream_t s) {
     switch (logn) {
 #define X(L) case L: if (kind == PIPE_R2C) fft_pipe_kernel<L, false, PIPE_R2C><<<grid, 2 * PIPE_GROUP, PIPE_SMEM, s>>>(a); \
                      else if (kind == PIPE_C2R) fft_pipe_kernel<L, true, PIPE_C2R><<<grid, 2 * PIPE_GROUP, PIPE_SMEM, s>>>(a); \
@@ -29,7 +29,9 @@ void launch_pipe_real(int logn, int kind, const PipeArgs& a, int grid, cudaStrea
                      else fft_pipe_kernel<L, true, PIPE_BLUE_INV><<<grid, 2 * PIPE_GROUP, PIPE_SMEM, s>>>(a); break;
         PIPE_CASES(X)
 #undef X
+        default: return cudaErrorInvalidValue;
     }
+    return cudaGetLastError();
 }
 
 const void* pipe_func(int logn, int inverse) {
@@ -41,12 +43,14 @@ const void* pipe_func(int logn, int inverse) {
     return nullptr;
 }
 
-void launch_pipe(int logn, const PipeArgs& a, int grid, cudaStream_t s) {
+cudaError_t launch_pipe(int logn, const PipeArgs& a, int grid, cudaStream_t s) {
     switch (logn) {
 #define X(L) case L: if (a.inverse) launch_pipe_t<L, true>(a, grid, s); else launch_pipe_t<L, false>(a, grid, s); break;
         PIPE_CASES(X)
 #undef X
+        default: return cudaErrorInvalidValue;
     }
+    return cudaGetLastError();
 }
 
 // N = 8192: two 4096-point halves per transform (fft_pipe13.cuh)

@@ -93,16 +93,18 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "WAIT_%=:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra DONE_%=;\n"
-        "bra WAIT_%=;\n"
-        "DONE_%=:\n"
-        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+// bounded wait: a lost bulk copy or a protocol error traps (the launch fails with an error the host reports) instead of
+// hanging the GPU; try_wait suspends the thread in hardware for a time slice, so the loop costs nothing while data flows
+__device__ __forceinline__ void mbar_wait_bounded(uint64_t* bar, uint32_t parity) {
+#pragma unroll 1
+    for (int it = 0; it < (1 << 24); it++) {
+        uint32_t ok;
+        asm volatile(
+            "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+            : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+        if (ok) return;
+    }
+    __trap();
 }
 // 1-D bulk async copy global -> shared, completion counted in bytes on `bar`
 __device__ __forceinline__ void bulk_load(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
@@ -209,7 +211,7 @@ __global__ void __launch_bounds__(2 * PIPE_GROUP, 1) fft_pipe_kernel(const PipeA
     uint32_t round = 0;        // k / PIPE_STAGES
     for (int k = g; k < my_tiles; k += 2) {
         cd* const sm = bufs + (size_t)b * PIPE_TILE;
-        mbar_wait(&full[b + PIPE_STAGES * (round & 1)], (round >> 1) & 1);
+        mbar_wait_bounded(&full[b + PIPE_STAGES * (round & 1)], (round >> 1) & 1);
         cd x[16];
         // ---- sub-pass 0: radix R0, exact constants, in place (each thread owns idx = t + 256 e) ----
 #pragma unroll

@@ -54,17 +54,49 @@ extern "C" const char* fftb200_last_error(void) { return g_err; }
 // ---------------------------------------------------------------------------------------------
 // per-device state
 // ---------------------------------------------------------------------------------------------
+// A twiddle table in device memory, shared by the device's cache and by every plan that points at it: the memory goes
+// away with the LAST reference, so fftb200_device_reset (fft_gpu_cleanup) or a larger table replacing it never pulls
+// a table from under a live plan.
+struct Table {
+    cd* ptr = nullptr;
+    int n = 0;
+    int refs = 1;
+};
 struct DeviceState {
     bool init = false;
     int sms = 0;
-    cd* tab = nullptr;   // largest twiddle table uploaded so far (older, smaller ones stay alive in `old`)
-    int tab_n = 0;
-    std::vector<cd*> old;
-    cd* acc = nullptr;   // accurate (correctly rounded) stage tables, fixed size ACC_N
+    Table* tab = nullptr;   // largest reference-recurrence table uploaded so far
+    Table* acc = nullptr;   // accurate (correctly rounded) stage tables, fixed size ACC_N
     char name[256] = "";
 };
 static DeviceState g_dev[64];
 static std::mutex g_mu;
+static int g_tables_alive = 0;   // diagnostics (fftb200_debug_tables_alive)
+
+static void table_release_locked(Table* t) {
+    if (t && --t->refs == 0) {
+        cudaFree(t->ptr);
+        delete t;
+        g_tables_alive--;
+    }
+}
+static void table_release(Table* t) {
+    if (!t) return;
+    std::lock_guard<std::mutex> lk(g_mu);
+    table_release_locked(t);
+}
+extern "C" int fftb200_debug_tables_alive(void) { std::lock_guard<std::mutex> lk(g_mu); return g_tables_alive; }
+
+// Plans remember their device: entry points that touch a plan switch to it for the duration of the call (a caller may
+// have moved on with fft_gpu_set_device) and switch back.
+struct DeviceGuard {
+    int prev = -1;
+    bool switched = false;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) == cudaSuccess && prev != dev && dev >= 0) switched = cudaSetDevice(dev) == cudaSuccess;
+    }
+    ~DeviceGuard() { if (switched) cudaSetDevice(prev); }
+};
 
 static int cur_device(DeviceState** ds) {
     int d = 0;
@@ -113,13 +145,10 @@ extern "C" int fftb200_device_reset(void) {
     std::lock_guard<std::mutex> lk(g_mu);
     if (cur_device(&s) != 0) return -1;
     CU(cudaDeviceSynchronize());
-    if (s->tab) cudaFree(s->tab);
-    if (s->acc) cudaFree(s->acc);
-    s->acc = nullptr;
-    for (cd* p : s->old) cudaFree(p);
-    s->old.clear();
+    table_release_locked(s->tab);   // freed now unless a live plan still uses it
+    table_release_locked(s->acc);
     s->tab = nullptr;
-    s->tab_n = 0;
+    s->acc = nullptr;
     return 0;
 }
 
@@ -248,6 +277,8 @@ struct fftb200_plan {
     std::vector<Pass> passes;  // forward or inverse c2c of length m over `batch`
     const cd* tab = nullptr;
     const cd* acc = nullptr;   // accurate tables (nullptr: reference-recurrence tables everywhere)
+    Table* tab_ref = nullptr;  // the shared tables `tab` / `acc` point into (one reference each, dropped by plan_destroy)
+    Table* acc_ref = nullptr;
     cd* scratch = nullptr;     // ping-pong buffer for multi-pass plans, allocated on first use
     size_t scratch_elems = 0;
     cd* fscratch = nullptr;    // fused plans: L2-resident ring of `slots` groups of transforms
@@ -314,6 +345,7 @@ static std::vector<int> split_passes(int log_n) {
 
 static int build_passes(fftb200_plan* p, DeviceState* ds) {
     const int L = p->log_n;
+    if (L == 0) { p->desc += "identity (one point)"; return 0; }   // no passes: enqueue_c2c copies (radix2_dit.c:59-120 leaves n = 1 untouched)
     std::vector<int> sizes = split_passes(L);
     const int np = (int)sizes.size();
     int log_m = 0;
@@ -639,6 +671,10 @@ static bool can_fuse_post(const fftb200_plan* p) { return p->passes.size() >= 2 
 static int enqueue_c2c(fftb200_plan* p, const cd* in, cd* out, int inverse, long long nbatch, const FuseSpec* pre = nullptr,
                        const FuseSpec* post = nullptr) {
     if (nbatch <= 0) return 0;
+    if (p->passes.empty()) {   // one-point transforms: X[0] = x[0] in both directions (1/n = 1)
+        if (in != out) CU(cudaMemcpyAsync(out, in, sizeof(cd) * (size_t)nbatch, cudaMemcpyDeviceToDevice, p->stream));
+        return 0;
+    }
     if (ensure_scratch(p, nbatch) != 0) return -1;
     for (const Pass& ps : p->passes) {
         const long long ntiles = pass_tiles(ps, nbatch);
@@ -658,7 +694,7 @@ static int enqueue_c2c(fftb200_plan* p, const cd* in, cd* out, int inverse, long
                 CU(launch_pipe13(pa, grid, p->stream));
                 continue;
             }
-            launch_pipe(ps.log_p, pa, grid, p->stream);
+            CU(launch_pipe(ps.log_p, pa, grid, p->stream));
             continue;
         }
         const cd* src = ps.src == BUF_IN ? in : ps.src == BUF_OUT ? out : p->scratch;
@@ -698,16 +734,20 @@ static int enqueue_c2c(fftb200_plan* p, const cd* in, cd* out, int inverse, long
 static int upload_table(fftb200_plan* p, DeviceState* ds, const fftb200_plan_desc* d, int need_n) {
     if (need_n <= 1) { p->tab = nullptr; return 0; }
     std::lock_guard<std::mutex> lk(g_mu);
-    if (ds->tab && ds->tab_n >= need_n) { p->tab = ds->tab; return 0; }
+    if (ds->tab && ds->tab->n >= need_n) { p->tab_ref = ds->tab; ds->tab->refs++; p->tab = ds->tab->ptr; return 0; }
     if (!d->twiddles || d->table_n < need_n) return fail("plan needs a twiddle table for size %d", need_n);
     cd* t = nullptr;
     size_t bytes = sizeof(cd) * (size_t)(d->table_n - 1);
     CU(cudaMalloc(&t, bytes ? bytes : 16));
-    CU(cudaMemcpy(t, d->twiddles, bytes, cudaMemcpyHostToDevice));
-    CU(cudaStreamSynchronize(cudaStreamLegacy));
-    if (ds->tab) ds->old.push_back(ds->tab);  // plans created earlier still point at it
-    ds->tab = t;
-    ds->tab_n = d->table_n;
+    if (cudaMemcpy(t, d->twiddles, bytes, cudaMemcpyHostToDevice) != cudaSuccess || cudaStreamSynchronize(cudaStreamLegacy) != cudaSuccess) {
+        cudaFree(t);
+        return fail("twiddle table upload failed: %s", cudaGetErrorString(cudaGetLastError()));
+    }
+    table_release_locked(ds->tab);   // plans created earlier keep their own reference to the smaller table
+    ds->tab = new Table();
+    ds->tab->ptr = t; ds->tab->n = d->table_n; ds->tab->refs = 2;   // the device cache + this plan
+    g_tables_alive++;
+    p->tab_ref = ds->tab;
     p->tab = t;
     return 0;
 }
@@ -721,11 +761,17 @@ static int upload_accurate(fftb200_plan* p, DeviceState* ds, const fftb200_plan_
         cd* t = nullptr;
         const size_t bytes = sizeof(cd) * (size_t)(ACC_N - 1);
         CU(cudaMalloc(&t, bytes));
-        CU(cudaMemcpy(t, d->twiddles_accurate, bytes, cudaMemcpyHostToDevice));
-        CU(cudaStreamSynchronize(cudaStreamLegacy));
-        ds->acc = t;
+        if (cudaMemcpy(t, d->twiddles_accurate, bytes, cudaMemcpyHostToDevice) != cudaSuccess || cudaStreamSynchronize(cudaStreamLegacy) != cudaSuccess) {
+            cudaFree(t);
+            return fail("accurate table upload failed: %s", cudaGetErrorString(cudaGetLastError()));
+        }
+        ds->acc = new Table();
+        ds->acc->ptr = t; ds->acc->n = ACC_N;
+        g_tables_alive++;
     }
-    p->acc = ds->acc;
+    ds->acc->refs++;
+    p->acc_ref = ds->acc;
+    p->acc = ds->acc->ptr;
     return 0;
 }
 
@@ -1043,6 +1089,13 @@ static int exec_range(fftb200_plan* p, const void* d_in, void* d_out, long long 
     const int inverse = p->dir > 0;
     if (p->kind == FFTB200_C2C) return enqueue_c2c(p, (const cd*)d_in, (cd*)d_out, inverse, nbatch);
     const size_t m = (size_t)p->m, n = (size_t)p->n, total = m * (size_t)nbatch;
+    if ((p->kind == FFTB200_R2C || p->kind == FFTB200_C2R) && (p->pipe_real || (p->kind == FFTB200_R2C && !p->work)) && nbatch > 0) {
+        // the single-kernel real transforms read packed rows that other CTAs' outputs would overwrite: out of place only
+        const size_t half = sizeof(cd) * (n / 2 + 1), full = sizeof(double) * n;
+        const char* i0 = (const char*)d_in; const char* o0 = (const char*)d_out;
+        const size_t ib = (p->kind == FFTB200_R2C ? full : half) * (size_t)nbatch, ob = (p->kind == FFTB200_R2C ? half : full) * (size_t)nbatch;
+        if (i0 < o0 + ob && o0 < i0 + ib) return fail("plan_exec: r2c / c2r plans of this size run out of place (input and output overlap)");
+    }
     if (p->pipe_real) {
         if (nbatch <= 0) return 0;
         const Pass& ps = p->passes[0];
@@ -1051,8 +1104,7 @@ static int exec_range(fftb200_plan* p, const void* d_in, void* d_out, long long 
         pa.in = (const cd*)d_in; pa.out = (cd*)d_out; pa.tab = p->acc;
         pa.ntiles = ntiles; pa.batch = nbatch;
         pa.inverse = p->kind == FFTB200_C2R; pa.scale = p->scale;
-        launch_pipe_real(ps.log_p, p->kind == FFTB200_R2C ? PIPE_R2C : PIPE_C2R, pa, (int)(ntiles < ps.grid_max ? ntiles : ps.grid_max), p->stream);
-        CU(cudaGetLastError());
+        CU(launch_pipe_real(ps.log_p, p->kind == FFTB200_R2C ? PIPE_R2C : PIPE_C2R, pa, (int)(ntiles < ps.grid_max ? ntiles : ps.grid_max), p->stream));
         return 0;
     }
     if (p->kind == FFTB200_C2R) {
@@ -1094,10 +1146,9 @@ static int exec_range(fftb200_plan* p, const void* d_in, void* d_out, long long 
         pa.tab = p->acc; pa.ntiles = ntiles; pa.batch = nbatch;
         pa.chirp = p->chirp; pa.fb = p->fb; pa.n_user = p->n; pa.y_scale = inverse ? 1.0 / (double)p->n : 1.0;
         pa.in = (const cd*)d_in; pa.out = p->work; pa.inverse = 0; pa.scale = 1.0;
-        launch_pipe_real(ps.log_p, PIPE_BLUE_FWD, pa, grid, p->stream);
+        CU(launch_pipe_real(ps.log_p, PIPE_BLUE_FWD, pa, grid, p->stream));
         pa.in = p->work; pa.out = (cd*)d_out; pa.inverse = 1; pa.scale = p->scale;
-        launch_pipe_real(ps.log_p, PIPE_BLUE_INV, pa, grid, p->stream);
-        CU(cudaGetLastError());
+        CU(launch_pipe_real(ps.log_p, PIPE_BLUE_INV, pa, grid, p->stream));
         return 0;
     }
     const bool fpre = can_fuse_pre(p), fpost = can_fuse_post(p);
@@ -1120,11 +1171,13 @@ static int exec_range(fftb200_plan* p, const void* d_in, void* d_out, long long 
 
 extern "C" int fftb200_plan_exec_async(fftb200_plan* p, const void* d_in, void* d_out) {
     if (!p || !d_in || !d_out) return fail("plan_exec: null argument");
+    DeviceGuard dg(p->device);
     return exec_range(p, d_in, d_out, p->batch);
 }
 
 extern "C" int fftb200_plan_sync(fftb200_plan* p) {
     if (!p) return fail("plan_sync: null plan");
+    DeviceGuard dg(p->device);
     CU(cudaStreamSynchronize(p->stream));
     return 0;
 }
@@ -1142,6 +1195,7 @@ extern "C" int fftb200_plan_exec(fftb200_plan* p, const void* d_in, void* d_out)
 // instead of their sum; pageable memory works too but serialises inside the driver.
 extern "C" int fftb200_plan_exec_host(fftb200_plan* p, const void* h_in, void* h_out) {
     if (!p || !h_in || !h_out) return fail("plan_exec_host: null argument");
+    DeviceGuard dg(p->device);
     const size_t half = sizeof(cd) * (size_t)(p->n / 2 + 1);
     const size_t in_per = p->kind == FFTB200_R2C ? sizeof(double) * (size_t)p->n : p->kind == FFTB200_C2R ? half : sizeof(cd) * (size_t)p->n;  // bytes / transform
     const size_t out_per = p->kind == FFTB200_R2C ? half : p->kind == FFTB200_C2R ? sizeof(double) * (size_t)p->n : sizeof(cd) * (size_t)p->n;
@@ -1182,16 +1236,32 @@ extern "C" int fftb200_plan_exec_host(fftb200_plan* p, const void* h_in, void* h
         long long cb = (long long)(target / per);
         if (cb < 1) cb = 1;
         if (cb > p->batch) cb = p->batch;
-        for (int i = 0; i < fftb200_plan::NSTAGE; i++) {
+        // all or nothing: a half-built ring must not survive into the next call (ring_batch == 0 would never advance the loop below)
+        bool ok = true;
+        for (int i = 0; i < fftb200_plan::NSTAGE && ok; i++) {
             p->d_ring[i] = (cd*)fftb200_malloc(per * (size_t)cb + 512);
-            if (!p->d_ring[i]) return -1;
-            if (cudaEventCreateWithFlags(&p->ev_up[i], cudaEventDisableTiming) != cudaSuccess ||
-                cudaEventCreateWithFlags(&p->ev_run[i], cudaEventDisableTiming) != cudaSuccess ||
-                cudaEventCreateWithFlags(&p->ev_down[i], cudaEventDisableTiming) != cudaSuccess) return fail("cudaEventCreate failed");
+            ok = p->d_ring[i] != nullptr &&
+                 cudaEventCreateWithFlags(&p->ev_up[i], cudaEventDisableTiming) == cudaSuccess &&
+                 cudaEventCreateWithFlags(&p->ev_run[i], cudaEventDisableTiming) == cudaSuccess &&
+                 cudaEventCreateWithFlags(&p->ev_down[i], cudaEventDisableTiming) == cudaSuccess;
+        }
+        if (!ok) {
+            const std::string why = g_err[0] ? g_err : "cudaEventCreate failed";
+            for (int i = 0; i < fftb200_plan::NSTAGE; i++) {
+                if (p->d_ring[i]) cudaFree(p->d_ring[i]);
+                if (p->ev_up[i]) cudaEventDestroy(p->ev_up[i]);
+                if (p->ev_run[i]) cudaEventDestroy(p->ev_run[i]);
+                if (p->ev_down[i]) cudaEventDestroy(p->ev_down[i]);
+                p->d_ring[i] = nullptr; p->ev_up[i] = nullptr; p->ev_run[i] = nullptr; p->ev_down[i] = nullptr;
+            }
+            p->ring_batch = 0;
+            cudaGetLastError();
+            return fail("plan_exec_host: staging ring setup failed (%s)", why.c_str());
         }
         p->ring_batch = (int)cb;
     }
     const long long cb = p->ring_batch;
+    if (cb <= 0) return fail("plan_exec_host: staging ring is not set up");
     const char* src = (const char*)h_in;
     char* dst = (char*)h_out;
     int c = 0;
@@ -1216,6 +1286,7 @@ extern "C" int fftb200_plan_exec_host(fftb200_plan* p, const void* h_in, void* h
 
 extern "C" void fftb200_plan_destroy(fftb200_plan* p) {
     if (!p) return;
+    DeviceGuard dg(p->device);
     if (p->stream) cudaStreamSynchronize(p->stream);
     if (p->s_down) cudaStreamSynchronize(p->s_down);
     if (p->scratch) cudaFree(p->scratch);
@@ -1237,6 +1308,8 @@ extern "C" void fftb200_plan_destroy(fftb200_plan* p) {
     if (p->stream && p->owns_stream) cudaStreamDestroy(p->stream);
     if (p->s_up) cudaStreamDestroy(p->s_up);
     if (p->s_down) cudaStreamDestroy(p->s_down);
+    table_release(p->tab_ref);
+    table_release(p->acc_ref);
     delete p;
 }
 
@@ -1273,11 +1346,13 @@ extern "C" int fftb200_pointwise_mul_conj(void* y, const void* a, const void* b,
 
 extern "C" int fftb200_timer_start(fftb200_plan* p) {
     if (!p) return fail("timer: null plan");
+    DeviceGuard dg(p->device);
     CU(cudaEventRecord(p->ev0, p->stream));
     return 0;
 }
 extern "C" int fftb200_timer_stop(fftb200_plan* p, float* ms) {
     if (!p || !ms) return fail("timer: null argument");
+    DeviceGuard dg(p->device);
     CU(cudaEventRecord(p->ev1, p->stream));
     CU(cudaEventSynchronize(p->ev1));
     CU(cudaEventElapsedTime(ms, p->ev0, p->ev1));

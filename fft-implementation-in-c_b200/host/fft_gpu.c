@@ -209,33 +209,139 @@ void fft_gpu_destroy_plan(fft_gpu_plan_t plan) {
     free(plan);
 }
 
-/* The host-pointer conveniences keep their last engine plan (tables, streams, staging ring): a caller that
- * loops over fft_gpu_dft_1d_batch with one shape - the reference's usage, gpu/fft_gpu.c:366-374 - pays for plan
- * construction once. One entry, guarded by a mutex that is held while the plan runs. */
-static struct { fftb200_plan* plan; int n, batch, dir, kind, device; } g_cache = {NULL, 0, 0, 0, 0, -1};
+/* The host-pointer conveniences keep their engine plans (tables, streams, staging ring, Bluestein chirp and kernel
+ * spectrum): a small LRU keyed on (device, n, batch, direction, kind). A caller that loops over fft_gpu_dft_1d_batch
+ * with one shape - the reference's usage, gpu/fft_gpu.c:366-374 - or alternates forward and inverse transforms - the
+ * convolution pattern, applications/convolution.c:34-96 - pays for plan construction once per shape. The mutex guards
+ * the table only: an entry is marked busy while its plan runs and the lock is released, so threads working on
+ * different shapes (or devices) run concurrently; a second thread asking for a shape that is busy builds a plan of its
+ * own, which joins the cache afterwards if a slot is free. */
+#define CACHE_SLOTS 16
+static struct cache_entry { fftb200_plan* plan; int n, batch, dir, kind, device, busy; unsigned long long stamp; } g_cache[CACHE_SLOTS];
+static unsigned long long g_cache_clock = 0;
+static long long g_cache_builds = 0, g_cache_hits = 0;
 static pthread_mutex_t g_cache_mu = PTHREAD_MUTEX_INITIALIZER;
 
 static void cache_drop(void) {
     pthread_mutex_lock(&g_cache_mu);
-    if (g_cache.plan) fftb200_plan_destroy(g_cache.plan);
-    g_cache.plan = NULL;
+    for (int i = 0; i < CACHE_SLOTS; i++) {
+        if (g_cache[i].plan && !g_cache[i].busy) { fftb200_plan_destroy(g_cache[i].plan); g_cache[i].plan = NULL; }
+    }
     pthread_mutex_unlock(&g_cache_mu);
+}
+
+/* diagnostics for tests: engine plans built / found by the cached host entry points since the process started */
+void fftb200_host_cache_stats(long long* builds, long long* hits) {
+    pthread_mutex_lock(&g_cache_mu);
+    if (builds) *builds = g_cache_builds;
+    if (hits) *hits = g_cache_hits;
+    pthread_mutex_unlock(&g_cache_mu);
+}
+
+static int exec_cached_on_current_device(const void* in, void* out, int n, int batch, int direction, int kind) {
+    const int dev = fftb200_get_device();
+    struct cache_entry* e = NULL;
+    pthread_mutex_lock(&g_cache_mu);
+    for (int i = 0; i < CACHE_SLOTS && !e; i++) {
+        struct cache_entry* c = &g_cache[i];
+        if (c->plan && !c->busy && c->n == n && c->batch == batch && c->dir == direction && c->kind == kind && c->device == dev) e = c;
+    }
+    if (e) { e->busy = 1; e->stamp = ++g_cache_clock; g_cache_hits++; }
+    pthread_mutex_unlock(&g_cache_mu);
+    fftb200_plan* plan = e ? e->plan : fftb200_host_make_plan(n, batch, direction, kind);   /* built outside the lock */
+    if (!plan) return -1;
+    const int rc = fftb200_plan_exec_host(plan, in, out);
+    if (rc != 0) report("host execute");
+    pthread_mutex_lock(&g_cache_mu);
+    if (e) {
+        e->busy = 0;
+    } else {
+        g_cache_builds++;
+        /* adopt the new plan: a free slot, else the least recently used idle one */
+        struct cache_entry* victim = NULL;
+        for (int i = 0; i < CACHE_SLOTS; i++) {
+            struct cache_entry* c = &g_cache[i];
+            if (c->busy) continue;
+            if (!c->plan) { victim = c; break; }
+            if (!victim || c->stamp < victim->stamp) victim = c;
+        }
+        fftb200_plan* old = NULL;
+        if (victim) {
+            old = victim->plan;
+            victim->plan = plan; victim->n = n; victim->batch = batch; victim->dir = direction; victim->kind = kind;
+            victim->device = dev; victim->busy = 0; victim->stamp = ++g_cache_clock;
+            plan = NULL;
+        }
+        pthread_mutex_unlock(&g_cache_mu);
+        if (old) fftb200_plan_destroy(old);
+        if (plan) fftb200_plan_destroy(plan);   /* every slot was busy: a private plan */
+        return rc == 0 ? 0 : -1;
+    }
+    pthread_mutex_unlock(&g_cache_mu);
+    return rc == 0 ? 0 : -1;
+}
+
+/* Multi-device fan-out of a batched host job (behind the unchanged fft_gpu_dft_1d_batch signature):
+ * FFTB200_GPUS=G (or fftb200_host_set_gpus) splits the batch into G contiguous ranges (fftb200_shard_range), one host
+ * thread per device, each with its own cached plan, streams and staging ring on that device; transforms are independent,
+ * so there is no exchange. The hook the reference offers for this is fft_gpu_set_device (include/fft_gpu.h:177). */
+static int g_host_gpus = 0;   /* 0: read FFTB200_GPUS once */
+void fftb200_host_set_gpus(int gpus) { g_host_gpus = gpus < 1 ? 1 : gpus; }
+int fftb200_host_get_gpus(void) {
+    if (g_host_gpus == 0) {
+        const char* e = getenv("FFTB200_GPUS");
+        int g = e ? atoi(e) : 1;
+        const int have = fftb200_device_count();
+        if (g > have) g = have;
+        g_host_gpus = g < 1 ? 1 : g;
+    }
+    return g_host_gpus;
+}
+
+struct fan_job { const char* in; char* out; int n, direction, kind, device, rc; long long first, count; size_t in_per, out_per; };
+
+static void* fan_worker(void* arg) {
+    struct fan_job* j = (struct fan_job*)arg;
+    j->rc = -1;
+    if (fftb200_set_device(j->device) != 0) return NULL;
+    j->rc = exec_cached_on_current_device(j->in + (size_t)j->first * j->in_per, j->out + (size_t)j->first * j->out_per, j->n, (int)j->count,
+                                          j->direction, j->kind);
+    return NULL;
 }
 
 int fftb200_host_exec_cached(const void* in, void* out, int n, int batch, int direction, int kind) {
     if (ensure_init() != 0) return -1;
-    const int dev = fftb200_get_device();
-    pthread_mutex_lock(&g_cache_mu);
-    if (!g_cache.plan || g_cache.n != n || g_cache.batch != batch || g_cache.dir != direction || g_cache.kind != kind ||
-        g_cache.device != dev) {
-        if (g_cache.plan) fftb200_plan_destroy(g_cache.plan);
-        g_cache.plan = fftb200_host_make_plan(n, batch, direction, kind);
-        g_cache.n = n; g_cache.batch = batch; g_cache.dir = direction; g_cache.kind = kind; g_cache.device = dev;
+    int gpus = fftb200_host_get_gpus();
+    /* below ~4 MiB per device the second device's launch + sync costs more than it saves */
+    const size_t half = sizeof(complex_t) * (size_t)(n / 2 + 1);
+    const size_t in_per = kind == FFTB200_R2C ? sizeof(double) * (size_t)n : kind == FFTB200_C2R ? half : sizeof(complex_t) * (size_t)n;
+    const size_t out_per = kind == FFTB200_R2C ? half : kind == FFTB200_C2R ? sizeof(double) * (size_t)n : sizeof(complex_t) * (size_t)n;
+    while (gpus > 1 && (batch < gpus || in_per * (size_t)batch / (size_t)gpus < ((size_t)4 << 20))) gpus--;
+    if (gpus <= 1) return exec_cached_on_current_device(in, out, n, batch, direction, kind);
+    const int home = fftb200_get_device();
+    struct fan_job jobs[64];
+    pthread_t th[64];
+    int spawned[64];
+    if (gpus > 64) gpus = 64;
+    int rc = 0;
+    for (int g = 0; g < gpus; g++) {
+        struct fan_job* j = &jobs[g];
+        j->in = (const char*)in; j->out = (char*)out; j->n = n; j->direction = direction; j->kind = kind;
+        j->device = (home + g) % fftb200_device_count();
+        j->in_per = in_per; j->out_per = out_per; j->rc = -1;
+        spawned[g] = 0;
+        fftb200_shard_range(batch, gpus, g, &j->first, &j->count);
+        if (j->count == 0) { j->rc = 0; continue; }
+        if (g == gpus - 1) { fan_worker(j); continue; }   /* the calling thread takes the last range */
+        if (pthread_create(&th[g], NULL, fan_worker, j) == 0) spawned[g] = 1;
+        else fan_worker(j);
     }
-    int rc = g_cache.plan ? fftb200_plan_exec_host(g_cache.plan, in, out) : -1;
-    if (rc != 0 && g_cache.plan) report("host execute");
-    pthread_mutex_unlock(&g_cache_mu);
-    return rc == 0 ? 0 : -1;
+    for (int g = 0; g < gpus; g++) {
+        if (spawned[g]) pthread_join(th[g], NULL);
+        if (jobs[g].rc != 0) rc = -1;
+    }
+    fftb200_set_device(home);
+    return rc;
 }
 
 int fft_gpu_dft_1d_batch(complex_t* in, complex_t* out, int n, int batch, fft_direction direction) {

@@ -24,6 +24,14 @@ void* fftb200_devptr_of(fft_gpu_memory_t mem);
  * transform more. Returns 0, or -1 on bad arguments. count may be 0 when world > batch. */
 int fftb200_shard_range(long long batch, int world, int rank, long long* first, long long* count);
 
+/* Multi-device fan-out of the batched host entry points (fft_gpu_dft_1d_batch and friends): with G > 1 the batch is cut
+ * into G contiguous ranges (fftb200_shard_range), one host thread, plan and staging ring per device, starting at the current
+ * device; no exchange step. Default 1, or the environment variable FFTB200_GPUS read at the first call. */
+void fftb200_host_set_gpus(int gpus);
+int fftb200_host_get_gpus(void);
+/* Diagnostics: engine plans built / re-used by the cached host entry points (fft_auto, fft_gpu_dft_1d_batch, ...). */
+void fftb200_host_cache_stats(long long* builds, long long* hits);
+
 const double* fftb200_host_twiddles(int n);           /* n - 1 complex, stage s entry j at 2^(s-1) - 1 + j */
 void fftb200_host_chirp(double* out, int n, int dir); /* n complex */
 void fftb200_host_tables_release(void);
