@@ -50,6 +50,7 @@ def parse_args():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--cpu-sample", type=int, default=16384, help="transforms per CPU step")
     ap.add_argument("--sweep", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the other BASELINE configs (cfg3 / cfg4 / cfg5 / size band)")
     return ap.parse_args()
 
 
@@ -181,19 +182,73 @@ def cpu_reference(n, sample, steps, warmup):
     return flops(n, sample) / t * 1e-9, t, kind, cores, desc
 
 
+def workload_name(n, batch):
+    return "batched c2c double FFT N=%d x %d batch per GPU (BASELINE configs[1])" % (n, batch)
+
+
+def cpu_others(n):
+    """The reference's own multi-threaded and SIMD CPU paths (optimizations/parallel_fft.c, simd_fft.c) timed beside the GPU, as
+    BASELINE.json's north_star asks: reported baselines only. They transform ONE array per call (no batch entry point), so each is
+    timed over repeated calls on the workload's N and on N = 2^20 (where threads can pay). ~3 s of CPU work in total."""
+    import numpy as np
+    from oracle import oracle as O
+    cores = os.cpu_count() or 1
+    out = []
+
+    def timed(fn, budget=0.35, min_reps=2):
+        fn()
+        reps, t0 = 0, time.perf_counter()
+        while reps < min_reps or time.perf_counter() - t0 < budget:
+            fn(); reps += 1
+        return (time.perf_counter() - t0) / reps, reps
+
+    try:
+        par, p = O.par(), O.port()
+        for nn in sorted({n, 1 << 20}):
+            if nn & (nn - 1):
+                continue
+            x = p.fill(43, 0, nn)
+            for name, fn in (("fft_radix2_parallel (optimizations/parallel_fft.c:130-210)", par.radix2_parallel),
+                             ("four_step_fft (optimizations/parallel_fft.c:213-272)", par.four_step)):
+                buf, flip = x.copy(), [1]
+
+                def call(fn=fn, buf=buf, flip=flip):   # forward and inverse alternate, so the values stay bounded
+                    flip[0] = -flip[0]
+                    fn(buf, flip[0], cores)
+                t, reps = timed(call)
+                out.append({"name": name, "n": nn, "value": flops(nn, 1) / t * 1e-9, "unit": "GFLOP/s", "cores": cores,
+                            "sample": "%d calls on one array of N=%d, %d threads, in place, forward / inverse alternating" % (reps, nn, cores)})
+    except Exception as e:  # noqa: BLE001
+        out.append({"name": "optimizations/parallel_fft.c", "value": None, "error": str(e)[:120]})
+    try:
+        sd = O.simd()
+        for nn in sorted({n, 1 << 20}):
+            if nn & (nn - 1):
+                continue
+            reps = max(4, min(2000, (1 << 24) // nn))
+            t = sd.sse2_seconds_per_transform(nn, reps)
+            out.append({"name": "fft_radix2_sse2 (optimizations/simd_fft.c:143-230)", "n": nn, "value": flops(nn, 1) / t * 1e-9,
+                        "unit": "GFLOP/s", "cores": 1, "dtype": "f32",
+                        "sample": "%d calls on one array of N=%d, single precision, output numerically wrong (SURVEY 6.2): timing only" % (reps, nn)})
+    except Exception as e:  # noqa: BLE001
+        out.append({"name": "optimizations/simd_fft.c", "value": None, "error": str(e)[:120]})
+    return out
+
+
 def main_reference(args, rank, world):
     if rank != 0:
         return
     steps = max(1, min(args.steps, 20))
-    gf, t, kind, cores, desc = cpu_reference(args.n, args.cpu_sample, steps, min(args.warmup, 2))
+    gf, t, kind, cores, desc = cpu_reference(args.n, args.cpu_sample, steps, args.warmup)
     line = {
         "impl": "reference", "metric": "batched c2c double FFT GFLOP/s (5*N*log2N*batch/t)", "value": gf, "unit": "GFLOP/s",
-        "n_gpus": args.gpus, "steps": steps, "warmup": min(args.warmup, 2), "ms_per_step": t * 1e3, "higher_is_better": True,
+        "n_gpus": args.gpus, "steps": steps, "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic (splitmix64 stream, seed 43)",
-        "config": {"workload": "batched c2c double FFT N=%d x %d batch per GPU" % (args.n, args.batch),
+        "config": {"workload": workload_name(args.n, args.batch),
                    "n": args.n, "batch_per_gpu": args.batch, "direction": "forward",
                    "note": "CPU arm runs a bounded sample of the batch per step; throughput is per transform, so it extrapolates"},
-        "cpu_baseline": {"value": gf, "unit": "GFLOP/s", "cores": cores, "kind": kind, "sample": desc},
+        "cpu_baseline": {"value": gf, "unit": "GFLOP/s", "cores": cores, "kind": kind, "sample": desc,
+                         "others": [] if args.no_cpu else cpu_others(args.n)},
         "e2e": {"value": gf, "unit": "GFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -220,6 +275,163 @@ def time_plan(L, eng, din, dout, steps, warmup, sync=None):
     return ms.value / steps
 
 
+def _rel_l2(a, b):
+    import numpy as np
+    return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300))
+
+
+def secondary_single(F, peak, din, dout, cap_elems):
+    """The other BASELINE configs that fit one GPU, timed in the same run through the engine C-ABI (CUDA events on the plan's
+    stream, 3 warm-ups + 10 executions) with a sampled parity check against the CPU oracle: cfg3 (2^24 single and x16), cfg5
+    (Bluestein 1000003 x1 / x16, r2c 2^20 x 256) and the north-star size band 2^10 .. 2^20 at 2^28 points. din / dout are the
+    headline's 4 GiB device buffers (cap_elems complex each), re-used."""
+    import numpy as np
+    from oracle import oracle as O
+    L, p = F.lib, O.port()
+    out = []
+
+    def run(tag, n, batch, kind, seed, bytes_per_transform, check_rows, flop_per_transform):
+        eng = F.engine_plan(n, batch, kind)
+        real_in = kind == F.FFTB200_R2C
+        in_elems = n * batch // 2 if real_in else n * batch         # complex elements of the input stream
+        assert in_elems <= cap_elems and (n // 2 + 1 if real_in else n) * batch <= cap_elems
+        L.fftb200_fill_splitmix(din, seed, 0, in_elems)
+        ms = time_plan(L, eng, din, dout, 10, 3)
+        rec = {"config": tag, "n": n, "batch": batch, "ms": ms, "strict_GBps": bytes_per_transform * batch / ms * 1e-6,
+               "frac": bytes_per_transform * batch / ms * 1e-6 / peak, "gflops": flop_per_transform * batch / ms * 1e-6,
+               "launches": L.fftb200_plan_launches(eng), "plan": L.fftb200_plan_describe(eng).decode()}
+        errs = []
+        for r in check_rows:
+            if real_in:
+                x = p.fill(seed, r * n // 2, n // 2).view(np.float64)
+                got = np.empty(n // 2 + 1, dtype=np.complex128)
+                L.fftb200_memcpy_d2h(F.ptr(got), dout + 16 * r * (n // 2 + 1), got.nbytes)
+                want = p.r2c(x)
+            else:
+                x = p.fill(seed, r * n, n)
+                got = np.empty(n, dtype=np.complex128)
+                L.fftb200_memcpy_d2h(F.ptr(got), dout + 16 * r * n, got.nbytes)
+                want = p.fft(x, -1)
+            errs.append(_rel_l2(got, want))
+        rec["rel_l2_vs_oracle"] = max(errs) if errs else None
+        rec["rows_checked"] = list(check_rows)
+        L.fftb200_plan_destroy(eng)
+        out.append(rec)
+
+    c2c = lambda n: 32.0 * n
+    fl = lambda n: 5.0 * n * math.log2(n)
+    run("cfg3: N=2^24 single", 1 << 24, 1, F.FFTB200_C2C, 44, c2c(1 << 24), [0], fl(1 << 24))
+    run("cfg3: N=2^24 x 16", 1 << 24, 16, F.FFTB200_C2C, 44, c2c(1 << 24), [15], fl(1 << 24))
+    nb = 1000003
+    run("cfg5: Bluestein n=1000003 single", nb, 1, F.FFTB200_BLUESTEIN, 46, c2c(nb), [0], fl(nb))
+    run("cfg5: Bluestein n=1000003 x 16", nb, 16, F.FFTB200_BLUESTEIN, 46, c2c(nb), [15], fl(nb))
+    nr = 1 << 20
+    run("cfg5: r2c N=2^20 x 256", nr, 256, F.FFTB200_R2C, 47, 8.0 * nr + 16.0 * (nr // 2 + 1), [0, 255], 2.5 * nr * 20)
+    for lg in range(10, 21):
+        n = 1 << lg
+        b = (1 << 28) >> lg
+        run("band: N=2^%d at 2^28 points" % lg, n, b, F.FFTB200_C2C, 43, c2c(n), [b - 1], fl(n))
+    return out
+
+
+def secondary_dist(F, rank, world, local_rank):
+    """BASELINE cfg4 scaled to the job: ONE transform of 2^(24 + 2 log2 G) points over the G GPUs (2^26 / 2^28 / 2^30 at 2 / 4 / 8)
+    through the C host API fftb200_dist_* (fused peer-store exchanges). Device-timed (max over ranks); every rank's block is compared
+    with the single-GPU plan of the whole transform (computed on rank 0, blocks broadcast) and, through the committed random-sign
+    sketch, with the REFERENCE ORACLE itself (tests/golden/oracle_2p*_sketch.npz, tests/sketch.py)."""
+    import importlib.util
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import fftb200_loader
+    L = F.lib
+    spec = importlib.util.spec_from_file_location("fft_b200_dist", os.path.join(fftb200_loader.PKG_DIR, "dist.py"))
+    D = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(D)
+    lw = int(math.log2(world))
+    lg = 24 + 2 * lw
+    n, nloc = 1 << lg, (1 << lg) // world
+    rec = {"config": "cfg4: ONE c2c transform of 2^%d points over %d GPUs (fftb200_dist_*, fused P2P exchanges)" % (lg, world), "log_n": lg}
+    t0 = time.time()
+    plan = D.DistFFTP2P(F, n, world, rank, direction=-1)
+    rec["plan_s"] = round(time.time() - t0, 2)
+    rec["plan"] = plan.describe
+    x = torch.empty(nloc, dtype=torch.complex128, device="cuda")
+    assert L.fftb200_fill_splitmix(x.data_ptr(), 45, rank * nloc, nloc) == 0
+    torch.cuda.synchronize()
+    y = plan.execute(x)
+    torch.cuda.synchronize()
+    ts = []
+    for it in range(5):
+        dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        y = plan.execute(x)
+        e1.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1)], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        if it >= 1:
+            ts.append(float(t))
+    ms = min(ts)
+    rec.update({"ms": ms, "ms_median": statistics.median(ts), "gflops": 5.0 * n * lg / ms * 1e-6, "strict_GBps_aggregate": 32.0 * n / ms * 1e-6})
+    # ---- parity 1: every rank's block against the single-GPU plan (rank 0 runs it, blocks are broadcast)
+    err2 = torch.zeros(2, dtype=torch.float64, device="cuda")
+    try:
+        ref = None
+        if rank == 0:
+            full = torch.empty(n, dtype=torch.complex128, device="cuda")
+            assert L.fftb200_fill_splitmix(full.data_ptr(), 45, 0, n) == 0
+            ref = torch.empty_like(full)
+            p1 = L.fft_gpu_plan_1d(n, 1, -1)
+            assert p1 and L.fftb200_plan_exec(L.fftb200_engine_of(p1), full.data_ptr(), ref.data_ptr()) == 0
+            L.fft_gpu_destroy_plan(p1)
+            del full
+        blk = torch.empty(nloc, dtype=torch.complex128, device="cuda")
+        for r in range(world):
+            if rank == 0:
+                blk.copy_(ref[r * nloc:(r + 1) * nloc])
+            dist.broadcast(torch.view_as_real(blk), src=0)
+            if r == rank:
+                d = y - blk
+                err2[0] = torch.sum(d.real * d.real + d.imag * d.imag)
+                err2[1] = torch.sum(blk.real * blk.real + blk.imag * blk.imag)
+        del blk, ref
+        per_rank = torch.zeros(world, dtype=torch.float64, device="cuda")
+        per_rank[rank] = torch.sqrt(err2[0] / err2[1])
+        dist.all_reduce(per_rank)
+        rec["rel_l2_vs_single_gpu_plan_per_rank"] = [float(v) for v in per_rank.cpu()]
+        rec["rel_l2"] = float(per_rank.max())
+    except Exception as e:  # noqa: BLE001 - the comparison needs 3 full-size arrays on rank 0; report instead of failing the bench
+        rec["rel_l2"] = None
+        rec["parity_error"] = repr(e)[:200]
+    # ---- parity 2: the reference oracle through the committed sketch
+    fx = os.path.join(ROOT, "tests", "golden", "oracle_2p%d_sketch.npz" % lg)
+    if os.path.exists(fx):
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import sketch
+        z = np.load(fx)
+        chunk = 1 << int(z["log_chunk"])
+        sk, en = sketch.sketch_torch(y, first=rank * nloc)
+        c0, c1 = rank * nloc // chunk, (rank + 1) * nloc // chunk
+        dd = np.abs(sk - z["sketch"][c0:c1]) ** 2
+        part = torch.tensor([dd.mean(axis=1).sum(), z["energy"][c0:c1].sum()], dtype=torch.float64, device="cuda")
+        dist.all_reduce(part)
+        rec["rel_l2_vs_reference_oracle_sketch"] = float(torch.sqrt(part[0] / part[1]))
+        small = os.path.join(ROOT, "tests", "golden", "oracle_2p%d_strided_small.npy" % lg)
+        if os.path.exists(small):
+            step = 1 << max(0, lg - 16)
+            want = np.load(small)[rank * nloc // step:(rank + 1) * nloc // step]
+            got = y[::step].cpu().numpy()
+            e = torch.tensor([float(np.sum(np.abs(got - want) ** 2)), float(np.sum(np.abs(want) ** 2))], dtype=torch.float64, device="cuda")
+            dist.all_reduce(e)
+            rec["rel_l2_vs_reference_oracle_strided_bins"] = float(torch.sqrt(e[0] / e[1]))
+            rec["strided_bins"] = 1 << min(16, lg)
+    plan.close()
+    return rec
+
+
 def main_b200(args, rank, world, local_rank):
     import fftb200_loader
     F = fftb200_loader.load()
@@ -229,7 +441,8 @@ def main_b200(args, rank, world, local_rank):
         import torch
         import torch.distributed as dist
         torch.cuda.set_device(local_rank)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        import datetime
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank), timeout=datetime.timedelta(seconds=300))
     if L.fft_gpu_available() != 1:
         raise SystemExit("bench.py: no CUDA device - the B200 path has no CPU fallback")
     if L.fft_gpu_set_device(local_rank) != 0 or L.fft_gpu_init(F.FFT_GPU_AUTO) != 0:
@@ -297,9 +510,20 @@ def main_b200(args, rank, world, local_rank):
         L.fft_free(hin)
         L.fft_free(hout)
 
+    secondary = None
+    if not args.no_secondary and world == 1 and total >= (1 << 28):
+        try:
+            secondary = secondary_single(F, hbm_peak()[0], din, dout, total)
+        except Exception as e:  # noqa: BLE001 - explanatory block: never takes the headline down
+            secondary = [{"error": repr(e)[:300]}]
     L.fft_gpu_destroy_plan(plan)
     L.fft_gpu_free(m_in)
     L.fft_gpu_free(m_out)
+    if not args.no_secondary and world > 1 and (world & (world - 1)) == 0:
+        try:
+            secondary = [secondary_dist(F, rank, world, local_rank)]
+        except Exception as e:  # noqa: BLE001
+            secondary = [{"config": "cfg4 distributed transform", "error": repr(e)[:300]}]
 
     if rank != 0:
         if dist is not None:
@@ -318,21 +542,26 @@ def main_b200(args, rank, world, local_rank):
         "unit": "GFLOP/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_max,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic (splitmix64 stream, seed 43, generated on the device)",
-        "config": {"workload": "batched c2c double FFT N=%d x %d batch per GPU (BASELINE configs[1])" % (n, batch),
+        "config": {"workload": workload_name(n, batch),
                    "n": n, "batch_per_gpu": batch, "direction": "forward", "plan": desc,
                    "l2": "input 32x larger than L2 (4 GiB vs 126 MB): no flush between iterations",
                    "parallelism": "batch sharded over %d GPU(s), no collective" % world},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": traffic, "peak_source": peak_src,
+                     "traffic": traffic, "traffic_source": "constant from one `ncu --set full` capture of this kernel "
+                     "(profiles/traffic.json, profiles/r01_n4096_b65536_ncu.md): dram__bytes_read.sum + dram__bytes_write.sum per launch; "
+                     "NOT measured in this run", "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": ms / launches_per_step},
         "clocks": clocks, "gpu_launches": launches_per_step * args.steps,
     }
     if e2e:
         line["e2e"] = e2e
+    if secondary is not None:
+        line["secondary"] = secondary
     if world == 1 and not args.no_cpu:
         try:
             gf, t, kind, cores, cdesc = cpu_reference(n, args.cpu_sample, 10, 1)
-            line["cpu_baseline"] = {"value": gf, "unit": "GFLOP/s", "cores": cores, "kind": kind, "sample": cdesc}
+            line["cpu_baseline"] = {"value": gf, "unit": "GFLOP/s", "cores": cores, "kind": kind, "sample": cdesc,
+                                    "others": cpu_others(n)}
         except Exception as e:  # the baseline is reported, never required for the product path
             line["cpu_baseline"] = {"value": None, "unit": "GFLOP/s", "cores": os.cpu_count(), "kind": "unavailable", "sample": str(e)}
     print(json.dumps(line), flush=True)

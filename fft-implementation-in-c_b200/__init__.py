@@ -113,6 +113,20 @@ _SIGS = {
     "fftb200_host_tables_release": (None, []),
     "fftb200_host_twiddles_dist": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_int]),
     "fftb200_shard_range": (C.c_int, [C.c_longlong, C.c_int, C.c_int, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]),
+    "fftb200_host_set_gpus": (None, [C.c_int]),
+    "fftb200_host_get_gpus": (C.c_int, []),
+    "fftb200_host_cache_stats": (None, [C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]),
+    "fftb200_barrier_create": (C.c_int, [C.POINTER(_vp), C.POINTER(_vp), C.c_int, C.c_int]),
+    "fftb200_barrier_enqueue": (C.c_int, [_vp, _vp]),
+    "fftb200_barrier_destroy": (None, [_vp]),
+    "fftb200_stream_sync": (C.c_int, [_vp]),
+    # include/fftb200_dist.h (argtypes with the callback are set by dist.py)
+    "fftb200_dist_choose_split": (C.c_int, [C.c_int, C.c_int]),
+    "fftb200_dist_sync": (C.c_int, [_vp]),
+    "fftb200_dist_stream": (_vp, [_vp]),
+    "fftb200_dist_log_m": (C.c_int, [_vp]),
+    "fftb200_dist_describe": (C.c_char_p, [_vp]),
+    "fftb200_dist_destroy": (None, [_vp]),
     "fft_gpu_convolution": (C.c_int, [_vp, C.c_int, _vp, C.c_int, _vp]),
     "fft_gpu_circular_convolution": (C.c_int, [_vp, _vp, C.c_int, _vp]),
     "fft_gpu_cross_correlation": (C.c_int, [_vp, _vp, C.c_int, _vp]),

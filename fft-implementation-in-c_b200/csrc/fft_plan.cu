@@ -1059,6 +1059,55 @@ extern "C" int fftb200_push_columns(const fftb200_peers* t, void* stream, const 
     return 0;
 }
 
+// Stream-ordered barrier between the ranks of a distributed transform, through peer memory instead of a collective library:
+// every rank owns a flag area (one 64-bit epoch per source rank, inside an IPC-exchanged buffer); the kernel stores the new
+// epoch into its slot of every peer's area (system-scope release) and spins until all slots of its own area have reached
+// it. Kernels enqueued before it on the stream have completed - their peer stores included - when it starts, and nothing
+// enqueued after it starts before every rank has arrived. All ranks must enqueue the same sequence of barriers.
+struct fftb200_barrier {
+    unsigned long long** d_flags = nullptr;   // device array: flag area of every rank as seen from this process
+    int world = 0, rank = 0;
+    unsigned long long epoch = 0;
+};
+__global__ void peer_barrier_kernel(unsigned long long* const* flags, int world, int rank, unsigned long long epoch) {
+    const int g = threadIdx.x;
+    if (g >= world) return;
+    __threadfence_system();
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(flags[g] + rank), "l"(epoch) : "memory");
+    const unsigned long long* mine = flags[rank] + g;
+    for (long long it = 0;; it++) {
+        unsigned long long v;
+        asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(mine) : "memory");
+        if (v >= epoch) break;
+        if (it > (1LL << 31)) __trap();   // a rank that never arrives fails the launch instead of hanging the GPU for good
+        __nanosleep(200);
+    }
+}
+extern "C" int fftb200_barrier_create(fftb200_barrier** out, void* const* flag_areas, int world, int rank) {
+    if (!out || !flag_areas || world < 1 || world > 64 || rank < 0 || rank >= world) return fail("barrier_create: bad argument");
+    fftb200_barrier* b = new fftb200_barrier();
+    b->world = world; b->rank = rank;
+    if (cudaMalloc(&b->d_flags, sizeof(void*) * world) != cudaSuccess ||
+        cudaMemcpy(b->d_flags, flag_areas, sizeof(void*) * world, cudaMemcpyHostToDevice) != cudaSuccess) {
+        cudaGetLastError(); delete b; return fail("barrier_create: device table failed");
+    }
+    *out = b;
+    return 0;
+}
+extern "C" int fftb200_barrier_enqueue(fftb200_barrier* b, void* stream) {
+    if (!b) return fail("barrier_enqueue: null barrier");
+    b->epoch++;
+    peer_barrier_kernel<<<1, 64, 0, (cudaStream_t)stream>>>(b->d_flags, b->world, b->rank, b->epoch);
+    CU(cudaGetLastError());
+    return 0;
+}
+extern "C" void fftb200_barrier_destroy(fftb200_barrier* b) {
+    if (!b) return;
+    if (b->d_flags) cudaFree(b->d_flags);
+    delete b;
+}
+extern "C" int fftb200_stream_sync(void* stream) { CU(cudaStreamSynchronize((cudaStream_t)stream)); return 0; }
+
 // CUDA IPC: one process per GPU, so peers' exchange buffers are mapped through handles exchanged by the caller
 extern "C" int fftb200_ipc_export(void* dptr, void* handle64) {
     if (!dptr || !handle64) return fail("ipc_export: null argument");

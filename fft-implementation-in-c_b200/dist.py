@@ -14,10 +14,12 @@ the reference's result (late-stage twiddles come from the reference recurrence, 
 
 Message shape per ordered GPU pair and exchange: N / G^2 complex doubles (256 MiB at N = 2^30, G = 8). Two drivers:
 
-  DistFFTP2P (the product)  the exchanges are FUSED into the kernels over NVSwitch peer memory: T0 is one push kernel,
-      T1 / T2 are the final scatter of the last head / tail pass, which stores straight into the peers' exchange
-      buffers (CUDA IPC mappings) in the layout the next local pass wants (csrc/fft_tile.cuh: peer_ptr). No NCCL
-      data movement and no separate transposes; NCCL only carries the three barriers between the phases.
+  DistFFTP2P (the product)  a thin binding of the C99 host API (include/fftb200_dist.h, host/fft_dist.c): the exchanges are
+      FUSED into the kernels over NVSwitch peer memory: T0 is one push kernel, T1 / T2 are the final scatter of the last
+      head / tail pass, which stores straight into the peers' exchange buffers (CUDA IPC mappings) in the layout the next
+      local pass wants (csrc/fft_tile.cuh: peer_ptr). No NCCL data movement, no separate transposes; the phases are
+      separated by the library's own peer-flag barrier kernel (fftb200_barrier_*), torch.distributed only all-gathers the
+      IPC handles at plan time.
   DistFFT (baseline, and the CPU-testable statement of the algebra)  each exchange is one NCCL all_to_all_single
       plus one local block permute (fftb200_permute_bac). It is written against a small backend interface so that
       the same index algebra runs on CPU tensors with the gloo backend (tests/test_dist_gloo.py; numpy stands in
@@ -90,6 +92,16 @@ class CudaBackend:
     def stream(self):
         return self.torch.cuda.stream(self.s_head)
 
+    def order_streams(self, before, tensors):
+        """x and the result live on torch's current stream, the passes run on the head plan's stream: order the two."""
+        cur = self.torch.cuda.current_stream()
+        if before:
+            self.s_head.wait_stream(cur)
+            for t in tensors:
+                t.record_stream(self.s_head)
+        else:
+            cur.wait_stream(self.s_head)
+
     def permute_bac(self, dst, src, A, B, Cc):
         if self.F.lib.fftb200_permute_bac(dst.data_ptr(), src.data_ptr(), A, B, Cc, self.s_head.cuda_stream) != 0:
             raise RuntimeError(self.F.lib.fftb200_last_error().decode())
@@ -137,8 +149,11 @@ class DistFFT:
     def execute(self, x, out=None):
         be, G = self.be, self.world
         Ml, Rl = self.M // G, self.R // G
+        sync = getattr(be, "order_streams", None)
         if out is None:
             out = be.empty()
+        if sync:
+            sync(before=True, tensors=(x, out))   # the plan's stream waits for the producer of x (and of out)
         with be.stream():
             if G > 1:
                 be.permute_bac(self.b0, x, Ml, G, Rl)             # [t_loc][g][r_loc] -> [g][t_loc][r_loc]
@@ -156,127 +171,92 @@ class DistFFT:
                 be.permute_bac(out, self.b0, G, Rl, Ml)           # -> [q_loc][s][k_loc] = X[k + M q], natural order
             else:
                 out.copy_(self.b1)
+        if sync:
+            sync(before=False, tensors=(x, out))  # the caller's stream waits for the result
         return out
 
     def close(self):
         self.be.close()
 
 
-class _DevBuf:
-    """A cudaMalloc'ed complex128 buffer (fftb200_malloc) exposed to torch through __cuda_array_interface__."""
+class _DevView:
+    """A device pointer owned by the library, exposed to torch through __cuda_array_interface__ (complex128, n elements)."""
 
-    def __init__(self, lib, n):
-        self.lib, self.n = lib, n
-        self.ptr = lib.fftb200_malloc(16 * n)
-        if not self.ptr:
-            raise MemoryError(lib.fftb200_last_error().decode())
-        self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<c16", "data": (self.ptr, False), "version": 2}
+    def __init__(self, ptr, n):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<c16", "data": (int(ptr), False), "version": 2}
 
     def tensor(self):
         import torch
         return torch.as_tensor(self, device="cuda")
 
-    def free(self):
-        if self.ptr:
-            self.lib.fftb200_free(self.ptr)
-            self.ptr = None
+
+_ALLGATHER = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t)
 
 
 class DistFFTP2P:
-    """Distributed transform with the exchanges fused into the kernels (P2P stores over NVLink / NVSwitch).
+    """The product path: a binding of the C99 host API fftb200_dist_* (include/fftb200_dist.h, host/fft_dist.c). The
+    exchanges are fused into the kernels (P2P stores over NVLink / NVSwitch), the phases are separated by the library's own
+    peer-flag barrier; torch.distributed only serves the plan-time all-gather of the IPC handles (the callback below).
 
     plan = DistFFTP2P(F, n_total, world, rank, direction); y = plan.execute(x_local)
-    y is a view of a buffer owned by the plan (natural order, this rank's block); it is overwritten by the next execute.
+    y is a view of a buffer owned by the plan (natural order, this rank's block). It is ordered after the transform on
+    torch's current stream and is OVERWRITTEN by the next execute() of any rank - consume or copy it before calling again.
     """
 
     def __init__(self, F, n_total, world, rank, direction=-1, log_m=None, group=None):
         import torch
         import torch.distributed as dist
-        self.torch, self.dist, self.F, self.group = torch, dist, F, group
+        self.torch, self.F, self.group = torch, F, group
         L = F.lib
-        lt, lw = int(math.log2(n_total)), int(math.log2(world))
-        if (1 << lt) != n_total or (1 << lw) != world:
+        lt = int(math.log2(n_total))
+        if (1 << lt) != n_total or (world & (world - 1)):
             raise ValueError("n_total and world must be powers of two")
-        self.n, self.world, self.rank = n_total, world, rank
-        self.log_m = choose_split(lt, lw) if log_m is None else log_m
-        self.M, self.R = 1 << self.log_m, 1 << (lt - self.log_m)
-        self.be = CudaBackend(F, n_total, world, rank, self.log_m, direction)   # head / tail partial plans + streams
-        nloc = n_total // world
-        self.e0, self.e1, self.e2 = _DevBuf(L, nloc), _DevBuf(L, nloc), _DevBuf(L, nloc)
-        # exchange the IPC handles of e0 (receives T0 and T2) and e2 (receives T1)
-        hs = torch.zeros(2, 64, dtype=torch.uint8)
-        for i, b in enumerate((self.e0, self.e2)):
-            buf = (C.c_ubyte * 64)()
-            if L.fftb200_ipc_export(b.ptr, buf) != 0:
-                raise RuntimeError(L.fftb200_last_error().decode())
-            hs[i] = torch.frombuffer(bytearray(buf), dtype=torch.uint8)
-        allh = [torch.zeros(2, 64, dtype=torch.uint8, device="cuda") for _ in range(world)]
-        if world > 1:
-            dist.all_gather(allh, hs.cuda(), group=group)
-        else:
-            allh[0] = hs.cuda()
-        self._mapped = []
-        self.peers = []
-        for i, own in enumerate((self.e0, self.e2)):
-            bases = (C.c_void_p * world)()
-            for g in range(world):
-                if g == rank:
-                    bases[g] = own.ptr
-                else:
-                    h = bytes(allh[g][i].cpu().numpy().tobytes())
-                    p = L.fftb200_ipc_open(h)
-                    if not p:
-                        raise RuntimeError("ipc_open: " + L.fftb200_last_error().decode())
-                    self._mapped.append(p)
-                    bases[g] = p
-            t = C.c_void_p()
-            if L.fftb200_peers_create(C.byref(t), bases, lw, rank) != 0:
-                raise RuntimeError(L.fftb200_last_error().decode())
-            self.peers.append(t)
-        Ml, Rl = self.M // world, self.R // world
-        self.lml, self.lrl = int(math.log2(Ml)), int(math.log2(Rl))
-        # head output [k][r_loc] -> rank k / Ml, B[k_loc][rank * Rl + r_loc];  tail output [q][k_loc] -> rank q / Rl, X[q_loc][rank * Ml + k_loc]
-        if L.fftb200_plan_set_peer_output(self.be.head, self.peers[1], self.lrl, self.lml) != 0 or \
-           L.fftb200_plan_set_peer_output(self.be.tail, self.peers[0], self.lml, self.lrl) != 0:
-            raise RuntimeError(L.fftb200_last_error().decode())
-        self._tok = torch.zeros(1, device="cuda")
-        self.out = self.e0.tensor()
+        self.n, self.world, self.rank, self.nloc = n_total, world, rank, n_total // world
+        L.fftb200_dist_create.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _ALLGATHER, C.c_void_p]
+        L.fftb200_dist_exec_async.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]
+        L.fftb200_dist_sync.argtypes = [C.c_void_p]
+        L.fftb200_dist_stream.argtypes = [C.c_void_p]
+        L.fftb200_dist_stream.restype = C.c_void_p
+        L.fftb200_dist_log_m.argtypes = [C.c_void_p]
+        L.fftb200_dist_describe.argtypes = [C.c_void_p]
+        L.fftb200_dist_describe.restype = C.c_char_p
+        L.fftb200_dist_destroy.argtypes = [C.c_void_p]
+        L.fftb200_dist_destroy.restype = None
 
-    def _barrier(self):
-        if self.world > 1:
-            self.dist.all_reduce(self._tok, group=self.group)   # stream-ordered: completes when every rank's earlier kernels have
+        def allgather(ctx, send, recv, nbytes):
+            try:
+                dev = "cuda" if dist.get_backend(group) == "nccl" else "cpu"
+                mine = torch.frombuffer(bytearray(C.string_at(send, nbytes)), dtype=torch.uint8).to(dev)
+                parts = [torch.empty(nbytes, dtype=torch.uint8, device=dev) for _ in range(world)]
+                dist.all_gather(parts, mine, group=group)
+                C.memmove(recv, torch.cat(parts).cpu().numpy().tobytes(), nbytes * world)
+                return 0
+            except Exception:  # noqa: BLE001 - reported through the return code of the C call
+                return -1
+        self._cb = _ALLGATHER(allgather)   # kept alive: the plan calls it again when it is destroyed
+        self.h = C.c_void_p()
+        if L.fftb200_dist_create(C.byref(self.h), lt, world, rank, direction, int(log_m or 0), self._cb, None) != 0:
+            raise RuntimeError("fftb200_dist_create: " + L.fftb200_last_error().decode())
+        self.log_m = L.fftb200_dist_log_m(self.h)
+        self.describe = L.fftb200_dist_describe(self.h).decode()
+        self.s = torch.cuda.ExternalStream(L.fftb200_dist_stream(self.h))
+
+    def stream(self):
+        return self.torch.cuda.stream(self.s)
 
     def execute(self, x):
-        L, be = self.F.lib, self.be
-        Ml = self.M // self.world
-        with be.stream():
-            self._barrier()                                                       # peers are done with the previous result
-            if L.fftb200_push_columns(self.peers[0], be.s_head.cuda_stream, x.data_ptr(), Ml, self.lrl) != 0:   # T0
-                raise RuntimeError(L.fftb200_last_error().decode())
-            self._barrier()
-            if L.fftb200_plan_exec_async(be.head, self.e0.ptr, self.e1.ptr) != 0:  # head, last pass stores into the peers' e2 (T1)
-                raise RuntimeError(L.fftb200_last_error().decode())
-            self._barrier()
-            ev = self.torch.cuda.Event()
-            ev.record(be.s_head)
-            be.s_tail.wait_event(ev)
-            if L.fftb200_plan_exec_async(be.tail, self.e2.ptr, self.e1.ptr) != 0:  # tail, last pass stores into the peers' e0 (T2)
-                raise RuntimeError(L.fftb200_last_error().decode())
-            ev2 = self.torch.cuda.Event()
-            ev2.record(be.s_tail)
-            be.s_head.wait_event(ev2)
-            self._barrier()
-        return self.out
+        t, L = self.torch, self.F.lib
+        cur = t.cuda.current_stream()
+        self.s.wait_stream(cur)            # x was produced on the caller's stream
+        x.record_stream(self.s)
+        out = C.c_void_p()
+        if L.fftb200_dist_exec_async(self.h, x.data_ptr(), C.byref(out)) != 0:
+            raise RuntimeError("fftb200_dist_exec_async: " + L.fftb200_last_error().decode())
+        cur.wait_stream(self.s)            # the result is ordered before whatever the caller enqueues next
+        return _DevView(out.value, self.nloc).tensor()
 
     def close(self):
-        L = self.F.lib
-        self.torch.cuda.synchronize()
-        if self.world > 1:
-            self.dist.barrier(group=self.group)
-        self.be.close()
-        for t in self.peers:
-            L.fftb200_peers_destroy(t)
-        for p in self._mapped:
-            L.fftb200_ipc_close(p)
-        for b in (self.e0, self.e1, self.e2):
-            b.free()
+        if self.h:
+            self.torch.cuda.synchronize()
+            self.F.lib.fftb200_dist_destroy(self.h)   # collective (meets the other ranks through the callback)
+            self.h = None

@@ -74,7 +74,9 @@ int fftb200_fill_splitmix(void* dst, unsigned long long seed, unsigned long long
 /* ---- plans ---- */
 int fftb200_plan_create(fftb200_plan** out, const fftb200_plan_desc* desc);
 /* d_in / d_out are device pointers (complex; R2C: d_in is n*batch doubles, d_out (n/2+1)*batch complex; C2R the
- * other way round). In place (d_in == d_out) is allowed for C2C, BLUESTEIN and C2R. Returns after the result is visible. */
+ * other way round). In place (d_in == d_out) is allowed for C2C and BLUESTEIN; R2C / C2R plans run out of place (the
+ * single-kernel real transforms read packed rows that other thread blocks' outputs would overwrite; overlapping
+ * buffers are rejected where that applies). Returns after the result is visible. */
 int fftb200_plan_exec(fftb200_plan* plan, const void* d_in, void* d_out);
 /* Same, but only enqueues on the plan's stream. */
 int fftb200_plan_exec_async(fftb200_plan* plan, const void* d_in, void* d_out);
@@ -116,6 +118,14 @@ int fftb200_plan_set_peer_output(fftb200_plan* plan, const fftb200_peers* peers,
 /* First exchange: push `rows` rows of 2^(log_width + log_world) elements, split by destination column block, into the
  * peers: rank g gets [rank * rows + t][c]. Enqueued on `stream` (a cudaStream_t). */
 int fftb200_push_columns(const fftb200_peers* peers, void* stream, const void* d_src, long long rows, int log_width);
+/* Stream-ordered barrier between the ranks through peer memory (no collective library): flag_areas[g] is rank g's flag area
+ * as seen from this process - at least 8 * world bytes inside an IPC-exchanged buffer, zeroed before the handles are
+ * exchanged. fftb200_barrier_enqueue puts one arrive-and-wait kernel on `stream`; every rank enqueues the same sequence. */
+typedef struct fftb200_barrier fftb200_barrier;
+int fftb200_barrier_create(fftb200_barrier** out, void* const* flag_areas, int world, int rank);
+int fftb200_barrier_enqueue(fftb200_barrier* barrier, void* stream);
+void fftb200_barrier_destroy(fftb200_barrier* barrier);
+int fftb200_stream_sync(void* stream);
 /* CUDA IPC handles (64 bytes) of buffers from fftb200_malloc, exchanged by the caller between the per-GPU processes */
 int fftb200_ipc_export(void* dptr, void* handle64);
 void* fftb200_ipc_open(const void* handle64);

@@ -7,6 +7,7 @@ The product package never does.
   ref()   -> oracle/_ref/libfftref.so  the UNMODIFIED reference CPU library (built by oracle/Makefile
              from /root/reference; prebuilt artefact on the GPU box)
   par()   -> oracle/_ref/libparref.so  the reference's pthreads/OpenMP path (CPU baseline timing only)
+  simd()  -> oracle/_ref/libsimdref.so the reference's SSE2 float path (CPU baseline timing only; numerically wrong)
 """
 import ctypes as C
 import os
@@ -204,6 +205,21 @@ class Par:
         self.lib.oracle_ref_four_step(_ptr(x.view(np.float64)), x.size, direction, threads)
 
 
+class Simd:
+    """Reference SIMD path (optimizations/simd_fft.c: fft_radix2_sse2, float, numerically wrong - SURVEY 6.2): TIMING ONLY."""
+
+    def __init__(self):
+        path = os.path.join(_HERE, "_ref", "libsimdref.so")
+        if not os.path.exists(path):
+            raise FileNotFoundError(path)
+        self.lib = L = C.CDLL(path)
+        L.oracle_ref_sse2_time.argtypes = [C.c_int, C.c_int]
+        L.oracle_ref_sse2_time.restype = C.c_double
+
+    def sse2_seconds_per_transform(self, n, reps):
+        return float(self.lib.oracle_ref_sse2_time(n, reps))
+
+
 class Apps:
     """The reference's FFT callers (applications/convolution.c, image_fft.c, power_spectrum.c), unmodified."""
 
@@ -276,6 +292,12 @@ def par():
     if "par" not in _cache:
         _cache["par"] = Par()
     return _cache["par"]
+
+
+def simd():
+    if "simd" not in _cache:
+        _cache["simd"] = Simd()
+    return _cache["simd"]
 
 
 def have_ref():

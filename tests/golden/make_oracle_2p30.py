@@ -41,7 +41,8 @@ def main():
     print(f"reference split_radix_fft in {time.time() - t0:.1f} s", flush=True)
     tag = f"oracle_2p{log_n}"
     step_big, step_small = 1 << max(0, log_n - 20), 1 << max(0, log_n - 16)
-    np.save(os.path.join(here, tag + "_strided.npy"), np.ascontiguousarray(x[::step_big]))
+    if log_n >= 30:   # 16 MiB, git-ignored; the smaller sizes keep the 1 MiB sample only
+        np.save(os.path.join(here, tag + "_strided.npy"), np.ascontiguousarray(x[::step_big]))
     np.save(os.path.join(here, tag + "_strided_small.npy"), np.ascontiguousarray(x[::step_small]))
     t0 = time.time()
     sk, en = sketch.sketch_numpy(x, first=0)

@@ -26,7 +26,7 @@ def declared_functions(header):
     return names
 
 
-@pytest.mark.parametrize("header", ["fft_auto.h", "fft_gpu.h", "fftb200.h", "fftb200_ext.h"])
+@pytest.mark.parametrize("header", ["fft_auto.h", "fft_gpu.h", "fftb200.h", "fftb200_ext.h", "fftb200_dist.h"])
 def test_every_declared_symbol_is_exported(F, header):
     if not os.path.exists(os.path.join(INC, header)):
         pytest.skip(header + " not present")
@@ -34,6 +34,33 @@ def test_every_declared_symbol_is_exported(F, header):
     assert len(names) >= 4, (header, names)
     missing = [n for n in names if not hasattr(F.lib, n)]
     assert not missing, missing
+
+
+# platform-specific hooks the reference declares only for other toolchains (Objective-C / nvcc) and defines nowhere for Linux gcc
+NOT_DECLARED_HERE = {"fft_gpu_set_mps_options", "fft_gpu_set_cuda_options"}
+
+
+@pytest.mark.parametrize("header", ["fft_auto.h", "fft_gpu.h"])
+def test_prototypes_match_the_reference_headers(header):
+    """Declaration by declaration against tests/golden/reference_prototypes.json (written from the reference's own headers by
+    tests/golden/make_prototypes.py): same return type and parameter types for every public function, same enum / flag values."""
+    import json
+    import proto_parse
+    ref = json.load(open(os.path.join(ROOT, "tests", "golden", "reference_prototypes.json")))
+    text = open(os.path.join(INC, header)).read()
+    mine = proto_parse.prototypes(text)
+    for name, sig in ref["prototypes"][header].items():
+        if name in NOT_DECLARED_HERE:
+            continue
+        assert mine.get(name) == sig, (name, sig, mine.get(name))
+    consts = proto_parse.constants(text)
+    if header == "fft_auto.h":   # the direction enum lives in fft_common.h in both trees
+        consts.update(proto_parse.constants(open(os.path.join(INC, "fft_common.h")).read()))
+        want = dict(ref["constants"]["fft_auto.h"], **ref["constants"]["fft_common.h"])
+    else:
+        want = ref["constants"][header]
+    for name, value in want.items():
+        assert consts.get(name) == value, (name, value, consts.get(name))
 
 
 def test_expected_public_names_present():

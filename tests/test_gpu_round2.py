@@ -1,0 +1,235 @@
+"""GPU suite, round 2 additions: every planner branch of csrc/fft_plan.cu (build_passes) against the oracle up to 2^28
+points, the host plan cache (LRU, concurrent shapes), the in-library multi-device fan-out, one-point transforms, the
+out-of-place rule of the single-kernel real transforms, cleanup with live plans.
+
+Bar as everywhere: relative L2 <= 1e-12 against the reference's CPU arithmetic (oracle/fft_oracle.c, pinned to the compiled
+reference by tests/test_oracle.py)."""
+import ctypes as C
+import threading
+import time
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-12
+
+
+def _describe(gpu, n, batch, direction=-1):
+    plan = gpu.engine_plan(n, batch, gpu.FFTB200_C2C, direction)
+    d = gpu.lib.fftb200_plan_describe(plan).decode()
+    gpu.lib.fftb200_plan_destroy(plan)
+    return d
+
+
+# (log_n, batch, substring the plan description must contain): one case per branch of build_passes
+BRANCHES = [
+    (21, 1, "F7"),            # 2^21 below 8 transforms: three tile passes
+    (21, 8, "Zc8+8"),         # 2^21 from 8 transforms: fused column head + L5
+    (22, 1, "F"),             # a single 2^22: three tile passes
+    (22, 2, "Zc8+8"),         # fused column head + L6
+    (23, 1, "Zc8+8"),
+    (25, 1, "Zc8+8"),         # + L9
+    (26, 1, "F9"),            # 2^26, 2^27: three tile passes of 8..9 stages
+    (27, 1, "F9"),
+    (28, 1, "F7"),            # four tile passes
+]
+
+
+@pytest.mark.parametrize("log_n,batch,tag", BRANCHES)
+def test_planner_branches_large_sizes_match_the_oracle(gpu, port, O, log_n, batch, tag):
+    n = 1 << log_n
+    desc = _describe(gpu, n, batch)
+    assert tag in desc, desc
+    x = port.fill(44, 0, n * batch).reshape(batch, n)
+    y = gpu.gpu_fft_batch(x, -1)
+    rows = sorted({0, batch - 1})
+    for r in rows:   # first and last transform against the oracle (seconds each on the host up to 2^28)
+        want = port.fft_batch(x[r:r + 1], -1)
+        assert O.rel_l2(y[r:r + 1], want) <= TOL, (log_n, batch, r, desc)
+    if log_n <= 25:
+        back = gpu.gpu_fft_batch(y, 1, inplace=True)
+        assert O.rel_l2(back, x) <= 1e-9     # the reference's own round trip drifts with its twiddle recurrence
+        assert O.rel_l2(back[:1], port.fft_batch(y[:1], 1)) <= TOL
+
+
+def test_one_point_transforms_are_the_identity(gpu):
+    x = np.array([[1.5 - 2.0j], [0.25 + 4.0j], [-3.0 + 0.5j]])
+    for d in (-1, 1):
+        assert np.array_equal(gpu.gpu_fft_batch(x, d), x)
+        assert np.array_equal(gpu.gpu_fft_batch(x, d, inplace=True), x)
+    assert np.array_equal(gpu.fft_auto(x[0], -1), x[0])
+    assert np.array_equal(gpu.fft2d(x[:1], -1), x[:1])
+
+
+def _stats(gpu):
+    b, h = C.c_longlong(), C.c_longlong()
+    gpu.lib.fftb200_host_cache_stats(C.byref(b), C.byref(h))
+    return b.value, h.value
+
+
+def test_plan_cache_keeps_both_directions_and_several_shapes(gpu, port, O):
+    """The convolution pattern: forward and inverse transforms of the same length alternate (and a Bluestein length in
+    between). After the first round nothing is rebuilt."""
+    x1 = port.fill(60, 0, 1024)
+    x2 = port.fill(61, 0, 1009)
+    for _ in range(2):   # warm: four shapes enter the cache
+        for x in (x1, x2):
+            for s in (-1, 1):
+                gpu.fft_auto(x, s)
+    b0, h0 = _stats(gpu)
+    reps = 50
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        y = gpu.fft_auto(x1, -1)
+        z = gpu.fft_auto(y, 1)
+    dt = (time.perf_counter() - t0) / (2 * reps)
+    for _ in range(5):
+        gpu.fft_auto(x2, -1); gpu.fft_auto(x2, 1)
+    b1, h1 = _stats(gpu)
+    assert b1 == b0, "a cached shape was rebuilt"
+    assert h1 - h0 == 2 * reps + 10
+    assert O.rel_l2(z, x1) <= 1e-12
+    assert O.rel_l2(gpu.fft_auto(x2, -1), port.fft(x2, -1)) <= TOL
+    print(f"fft_auto(1024) alternating directions: {dt * 1e6:.1f} us per call (ctypes overhead included)")
+    assert dt < 200e-6
+
+
+def test_two_threads_with_different_shapes_run_concurrently(gpu, port, O):
+    shapes = [(4096, 512), (1 << 15, 64)]
+    xs = [port.fill(62 + i, 0, n * b).reshape(b, n) for i, (n, b) in enumerate(shapes)]
+    outs = [np.empty_like(x) for x in xs]
+    errs = []
+
+    def work(i):
+        n, b = shapes[i]
+        for _ in range(6):
+            rc = gpu.lib.fft_gpu_dft_1d_batch(gpu.ptr(xs[i]), gpu.ptr(outs[i]), n, b, -1)
+            if rc != 0:
+                errs.append((i, rc))
+
+    th = [threading.Thread(target=work, args=(i,)) for i in range(2)]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    assert not errs
+    for x, y in zip(xs, outs):
+        rows = [0, x.shape[0] - 1]
+        assert O.rel_l2(y[rows], port.fft_batch(x[rows], -1)) <= TOL
+
+
+def test_same_shape_from_two_threads(gpu, port, O):
+    """A busy cache entry is not shared: the second thread gets a plan of its own."""
+    n, b = 2048, 256
+    x = port.fill(64, 0, n * b).reshape(b, n)
+    want = port.fft_batch(x[:2], -1)
+    outs = [np.empty_like(x) for _ in range(3)]
+    rcs = [None] * 3
+
+    def work(i):
+        for _ in range(4):
+            rcs[i] = gpu.lib.fft_gpu_dft_1d_batch(gpu.ptr(x), gpu.ptr(outs[i]), n, b, -1)
+
+    th = [threading.Thread(target=work, args=(i,)) for i in range(3)]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    assert rcs == [0, 0, 0]
+    for y in outs:
+        assert O.rel_l2(y[:2], want) <= TOL
+        assert np.array_equal(y, outs[0])
+
+
+@pytest.mark.parametrize("n,batch", [(4096, 4099), (1 << 16, 301), (1009, 4000)])
+def test_multi_device_fan_out_behind_the_batch_entry_point(gpu, port, O, n, batch):
+    """fftb200_host_set_gpus(G): fft_gpu_dft_1d_batch cuts the batch into G ranges, one host thread + plan + staging ring per
+    device (devices wrap around when the box has fewer, so a 1-GPU box runs the same code with both ranges on device 0)."""
+    x = port.fill(65, 0, n * batch).reshape(batch, n)
+    one = np.empty_like(x)
+    gpu.lib.fftb200_host_set_gpus(1)
+    assert gpu.lib.fft_gpu_dft_1d_batch(gpu.ptr(x), gpu.ptr(one), n, batch, -1) == 0
+    try:
+        for g in (2, 3):
+            gpu.lib.fftb200_host_set_gpus(g)
+            assert gpu.lib.fftb200_host_get_gpus() == g
+            out = np.zeros_like(x)
+            assert gpu.lib.fft_gpu_dft_1d_batch(gpu.ptr(x), gpu.ptr(out), n, batch, -1) == 0
+            assert np.array_equal(out, one)
+    finally:
+        gpu.lib.fftb200_host_set_gpus(1)
+    rows = [0, batch // 2, batch - 1]
+    want = np.stack([port.fft(x[r], -1) for r in rows])
+    assert O.rel_l2(one[rows], want) <= TOL
+
+
+@pytest.mark.parametrize("n", [512, 4096, 1 << 14])
+def test_single_kernel_real_transforms_reject_overlapping_buffers(gpu, port, n):
+    """r2c / c2r plans whose kernel reads packed rows (pipe variants 512 .. 4096, fused r2c) run out of place: an aliased call fails
+    with an error instead of racing."""
+    import torch
+    L = gpu.lib
+    batch = 40
+    buf = torch.zeros(batch * (n + 2), dtype=torch.complex128, device="cuda")
+    p = gpu.engine_plan(n, batch, gpu.FFTB200_R2C)
+    assert L.fftb200_plan_exec(p, buf.data_ptr(), buf.data_ptr()) != 0
+    assert b"out of place" in L.fftb200_last_error()
+    assert L.fftb200_plan_exec(p, buf.data_ptr(), buf.data_ptr() + 16 * batch * n) == 0
+    L.fftb200_plan_destroy(p)
+    if n <= 4096:
+        p = gpu.engine_plan(n, batch, gpu.FFTB200_C2R, 1)
+        assert L.fftb200_plan_exec(p, buf.data_ptr(), buf.data_ptr()) != 0
+        L.fftb200_plan_destroy(p)
+
+
+def test_c2r_in_place_where_it_is_allowed(gpu, port, O):
+    """c2r outside the single-kernel sizes goes through the plan's work array: in place is fine."""
+    import torch
+    L = gpu.lib
+    n, batch = 1 << 15, 9
+    x = port.fill(66, 0, n * batch).real.copy().reshape(batch, n)
+    half = np.fft.rfft(x, axis=1)
+    p = gpu.engine_plan(n, batch, gpu.FFTB200_C2R, 1)
+    buf = torch.zeros(batch * n, dtype=torch.complex128, device="cuda")   # room for either side
+    buf[:half.size] = torch.from_numpy(half.ravel()).cuda()
+    assert L.fftb200_plan_exec(p, buf.data_ptr(), buf.data_ptr()) == 0
+    got = torch.view_as_real(buf).ravel()[:batch * n].cpu().numpy().reshape(batch, n)
+    assert O.rel_l2(got, x) <= 1e-11
+    L.fftb200_plan_destroy(p)
+
+
+def test_cleanup_keeps_the_tables_of_live_plans(gpu, port, O):
+    """fft_gpu_cleanup drops the device's cached twiddle tables; a plan created before it still owns a reference."""
+    L = gpu.lib
+    n, b = 1 << 16, 5
+    x = port.fill(67, 0, n * b).reshape(b, n)
+    plan = L.fft_gpu_plan_1d(n, b, -1)
+    m = L.fft_gpu_alloc(n * b)
+    L.fft_gpu_copy_h2d(m, gpu.ptr(x), n * b)
+    L.fft_gpu_cleanup()
+    gpu.require_gpu()
+    other = gpu.gpu_fft_batch(port.fill(68, 0, 1 << 18).reshape(1, -1), -1)   # new tables get uploaded meanwhile
+    assert other.shape == (1, 1 << 18)
+    L.fft_gpu_execute(plan, m, m)
+    out = np.empty_like(x)
+    L.fft_gpu_copy_d2h(gpu.ptr(out), m, n * b)
+    assert O.rel_l2(out, port.fft_batch(x, -1)) <= TOL
+    L.fft_gpu_destroy_plan(plan)
+    L.fft_gpu_free(m)
+
+
+def test_plan_follows_its_device(gpu, port, O):
+    """A plan created on device A still runs on A after the caller moved on with fft_gpu_set_device (needs 2 GPUs)."""
+    L = gpu.lib
+    if L.fftb200_device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    n, b = 4096, 64
+    x = port.fill(69, 0, n * b).reshape(b, n)
+    plan = L.fft_gpu_plan_1d(n, b, -1)
+    m = L.fft_gpu_alloc(n * b)
+    L.fft_gpu_copy_h2d(m, gpu.ptr(x), n * b)
+    assert L.fft_gpu_set_device(1) == 0
+    L.fft_gpu_execute(plan, m, m)
+    assert L.fft_gpu_set_device(0) == 0
+    out = np.empty_like(x)
+    L.fft_gpu_copy_d2h(gpu.ptr(out), m, n * b)
+    assert O.rel_l2(out, port.fft_batch(x, -1)) <= TOL
+    L.fft_gpu_destroy_plan(plan)
+    L.fft_gpu_free(m)

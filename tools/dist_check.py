@@ -37,7 +37,7 @@ for lg in logs:
         torch.cuda.synchronize()
         y = plan.execute(x)
         torch.cuda.synchronize()
-        res = {"driver": "nccl" if "--nccl" in sys.argv else "p2p", "log_n": lg, "world": world, "rank": rank, "dir": direction, "log_m": plan.log_m, "plan_s": round(t_plan, 2), "passes": plan.be.describe}
+        res = {"driver": "nccl" if "--nccl" in sys.argv else "p2p", "log_n": lg, "world": world, "rank": rank, "dir": direction, "log_m": plan.log_m, "plan_s": round(t_plan, 2), "passes": plan.describe if hasattr(plan, "describe") else plan.be.describe}
         if "--noparity" not in sys.argv and n * 16 * 3 < 120e9 and (lg < 30 or rank == 0):
           try:
             full = torch.empty(n, dtype=torch.complex128, device="cuda")
@@ -51,18 +51,43 @@ for lg in logs:
             del full, ref
           except Exception as e:  # the comparison is best effort at the largest size (host table + 3 full-size device arrays)
             res["parity_error"] = repr(e)[:200]
+        if "--oracle" in sys.argv and direction == -1:
+            # the reference oracle itself (unmodified split_radix_fft on the host, tests/golden/make_oracle_2p30.py): exact strided
+            # bins of this rank's block + the random-sign sketch of the whole block (tests/sketch.py)
+            sys.path.insert(0, os.path.join(os.path.dirname(__file__), "..", "tests"))
+            import sketch
+            gold = os.path.join(os.path.dirname(__file__), "..", "tests", "golden")
+            fx = os.path.join(gold, f"oracle_2p{lg}_sketch.npz")
+            if os.path.exists(fx):
+                z = np.load(fx)
+                assert int(z["log_n"]) == lg and int(z["seed"]) == 45
+                chunk = 1 << int(z["log_chunk"])
+                sk, en = sketch.sketch_torch(y, first=rank * nloc)
+                c0, c1 = rank * nloc // chunk, (rank + 1) * nloc // chunk
+                res["oracle_sketch_rel_l2"] = sketch.rel_l2_estimate(sk, z["sketch"][c0:c1], z["energy"][c0:c1])
+                res["oracle_energy_rel"] = float(abs(en.sum() - z["energy"][c0:c1].sum()) / z["energy"][c0:c1].sum())
+                for name, lstep in (("strided", max(0, lg - 20)), ("strided_small", max(0, lg - 16))):
+                    f2 = os.path.join(gold, f"oracle_2p{lg}_{name}.npy")
+                    if os.path.exists(f2):
+                        ref_bins = np.load(f2, mmap_mode="r")
+                        step = 1 << lstep
+                        mine = np.asarray(ref_bins[rank * nloc // step:(rank + 1) * nloc // step])
+                        got = y[::step].cpu().numpy()
+                        res[f"oracle_{name}_bins"] = int(mine.size)
+                        res[f"oracle_{name}_rel_l2"] = float(np.linalg.norm(got - mine) / np.linalg.norm(mine))
+                        res[f"oracle_{name}_max_abs"] = float(np.abs(got - mine).max())
+            else:
+                res["oracle"] = "fixture missing: " + os.path.basename(fx)
         if "--notime" not in sys.argv:
             ts = []
             for it in range(6):
                 if world > 1: dist.barrier()
                 torch.cuda.synchronize()
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                with plan.be.stream():
-                    e0.record(); 
+                e0.record()   # execute() orders the plan's stream after / before torch's current stream
                 if "--nccl" in sys.argv: plan.execute(x, y)
                 else: plan.execute(x)
-                with plan.be.stream():
-                    e1.record()
+                e1.record()
                 torch.cuda.synchronize()
                 t = torch.tensor([e0.elapsed_time(e1)], device="cuda")
                 if world > 1: dist.all_reduce(t, op=dist.ReduceOp.MAX)
