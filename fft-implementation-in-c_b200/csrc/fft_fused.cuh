@@ -175,6 +175,9 @@ __device__ __forceinline__ void tma_store_3d(const CUtensorMap* tm, int c0, int 
 __device__ __forceinline__ void bulk_store(void* dst, const void* src, uint32_t bytes) {
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(src)), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ void bulk_store_hint(void* dst, const void* src, uint32_t bytes, uint64_t pol) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;" ::"l"(dst), "r"(smem_u32(src)), "r"(bytes), "l"(pol) : "memory");
+}
 __device__ __forceinline__ void bulk_load_hint(void* dst, const void* src, uint32_t bytes, uint64_t* bar, uint64_t pol) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
                  ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(pol) : "memory");
@@ -186,15 +189,17 @@ __device__ __forceinline__ void bulk_load_hint(void* dst, const void* src, uint3
 struct FusedSched {
     long long nbatch;
     int gt, G, L, log_tpt, a_on, b_on;
-    __device__ __forceinline__ long long tiles_of(int g) const {
+    int tpb;   // pass-B tiles per transform: 2^log_tpt, or 2^(log_tpt - 1) + 1 when only the columns k <= M/2 are transformed (real input)
+    __device__ __forceinline__ long long transforms_of(int g) const {
         long long nb = nbatch - (long long)g * gt;
-        if (nb > gt) nb = gt;
-        return nb << log_tpt;
+        return nb > gt ? gt : nb;
     }
+    __device__ __forceinline__ long long tiles_of(int g) const { return transforms_of(g) << log_tpt; }   // pass A
+    __device__ __forceinline__ long long tiles_b(int g) const { return transforms_of(g) * tpb; }        // pass B
     __device__ __forceinline__ long long round_len(int rho) const {
         long long n = 0;
         if (a_on && rho < G) n += tiles_of(rho);
-        if (b_on && rho >= L && rho - L < G) n += tiles_of(rho - L);
+        if (b_on && rho >= L && rho - L < G) n += tiles_b(rho - L);
         return n;
     }
 };
@@ -257,19 +262,31 @@ __device__ __forceinline__ cd cmul2(const cd a, const cd b) {
 // product with d[h] = T[a_tot + s][q << a_tot], the table's own entry at kappa = 0. The reference recurrence
 // w_j = fl(w_(j-1) w_m) (radix2_dit.c:93,109) makes its table multiplicative up to rounding noise, so the product
 // reproduces the reference's accumulated twiddle drift: whole-transform mismatch 1.3e-14 at N = 2^20.
+// Measured and not kept (r02, same-box A/B at 2^28 points): issuing the loads one exchange ahead of the butterflies they feed
+// (right after the previous sub-pass's butterflies, 16 registers in flight across two group barriers, a scatter and a gather).
+// Pass-B tiles are 2 200 - 3 300 cycles slower than pass-A tiles (FUSED_PROF), but the early loads cost more in register
+// pressure than they hide: 2^14 2.34 -> 2.29 ms, 2^16 2.24 -> 2.30, 2^17 2.40 -> 2.57, 2^18 2.60 -> 2.87, 2^20 2.92 -> 3.29.
 template <int R>
-__device__ __forceinline__ void fused_twiddles(cd* tw, const cd* tp, const int a_tot, const cd* d) {
+__device__ __forceinline__ void fused_tw_load(cd* raw, const cd* tp, const int a_tot) {
 #pragma unroll
-    for (int s = 1; s <= R; s++) {
-        const int h0 = 1 << (s - 1);
-        tw[h0] = __ldg(tp + ((size_t)h0 << a_tot));
-    }
+    for (int s = 1; s <= R; s++) raw[s - 1] = __ldg(tp + ((size_t)1 << (s - 1 + a_tot)));
+}
+template <int R>
+__device__ __forceinline__ void fused_tw_expand(cd* tw, const cd* raw, const cd* d) {
+#pragma unroll
+    for (int s = 1; s <= R; s++) tw[1 << (s - 1)] = raw[s - 1];
 #pragma unroll
     for (int s = 2; s <= R; s++) {
         const int h0 = 1 << (s - 1);
 #pragma unroll
         for (int q = 1; q < h0; q++) tw[h0 + q] = cmul2(tw[h0], d[h0 + q]);
     }
+}
+template <int R>
+__device__ __forceinline__ void fused_twiddles(cd* tw, const cd* tp, const int a_tot, const cd* d) {
+    cd raw[R];
+    fused_tw_load<R>(raw, tp, a_tot);
+    fused_tw_expand<R>(tw, raw, d);
 }
 // a compute warp has written its part of the result tile into the ring buffer: make the writes visible to the
 // async proxy (the TMA store reads them) and arrive once per warp on the buffer's `staged` barrier
@@ -295,16 +312,26 @@ __device__ __forceinline__ void fused_publish(int* counter) {
 // fft_plan_r2c_1d without the separate promotion and extraction passes.
 // C2R (inverse only): the input is the Hermitian-extended spectrum (c2r_expand_kernel), only the real parts of the result are
 // staged and stored (n doubles per transform, fft_auto.h:99-107): the separate real-part pass and its 24 bytes per point go away.
-template <int LM, int LR, bool INV, bool COLS = false, bool R2C = false, bool C2R = false>
+template <int LM, int LR, bool INV, bool COLS = false, bool R2C = false, bool C2R = false, bool HERM = false>
 __global__ void __launch_bounds__(FUSED_THREADS, 1)
 fft_fused_kernel(const FusedArgs a, const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUtensorMap tm_sc,
-                 const __grid_constant__ CUtensorMap tm_out) {
+                 const __grid_constant__ CUtensorMap tm_out, const __grid_constant__ CUtensorMap tm_out2) {
     static_assert(LM >= 6 && LM <= 10 && LR >= 6 && LR <= 10, "pass sizes 64 .. 1024");
     static_assert(!COLS || (LM == 8 && LR == 8), "column mode is built for 256 x 256");
     static_assert(!R2C || (!INV && !COLS), "r2c is a forward transform of whole arrays");
     static_assert(!C2R || (INV && !COLS && !R2C), "c2r is an inverse transform of whole arrays");
+    static_assert(!HERM || R2C, "the Hermitian schedule is a variant of r2c");
     constexpr int LOGN = COLS ? 20 : LM + LR;             // points per (virtual) transform
     constexpr int LOG_TPT = LOGN - 12;
+    // HERM: r2c with a Hermitian-aware schedule: the pass-A outputs of a real column satisfy Y_c[M - k] = conj(Y_c[k]), so only the
+    // rows k <= M/2 go to scratch and pass B transforms only those columns: TPB = tiles/2 + 1 tiles per transform instead of
+    // 2^LOG_TPT (the last one holds the single column k = M/2). A column k yields the bins k + M q directly for q < R/2 and, as
+    // conjugates, the bins (M - k) + M (R - 1 - q) of the column M - k for q >= R/2 (X[N - j] = conj(X[j])): every bin 0 .. N/2 is
+    // produced with half of the pass-B work and scratch traffic. The mirrored bins are NOT the reference's own X[N - j]: its twiddle
+    // recurrence (radix2_dit.c:93,109) is not conjugate-symmetric, so its output for real input is Hermitian only to the accuracy of
+    // its late-stage twiddles. Measured mismatch against the oracle (profiles/r02_real.md) decides which sizes run this schedule;
+    // the others keep the full pass B (R2C without HERM: every column transformed, rows q < R/2 stored).
+    constexpr int TPB = HERM ? (1 << (LOG_TPT - 1)) + 1 : (1 << LOG_TPT);
     constexpr int LC = 12 - LM, LC2 = 12 - LR;          // log2 columns per A tile / k's per B tile
     constexpr int A3 = LM >= 9, B3 = LR >= 9;            // three sub-passes?
     constexpr int RA0 = A3 ? LM - 8 : LM - 4, RB0 = B3 ? LR - 8 : LR - 4;
@@ -325,10 +352,10 @@ fft_fused_kernel(const FusedArgs a, const __grid_constant__ CUtensorMap tm_in, c
     volatile int* const kinds = reinterpret_cast<volatile int*>(staged + PIPE_STAGES);   // [3][4]: is_b, kb, g of the loaded tile
 
     FusedSched sch;
-    sch.nbatch = a.nbatch; sch.gt = a.gt; sch.G = a.ngroups; sch.L = a.lag; sch.log_tpt = LOG_TPT;
+    sch.nbatch = a.nbatch; sch.gt = a.gt; sch.G = a.ngroups; sch.L = a.lag; sch.log_tpt = LOG_TPT; sch.tpb = TPB;
     sch.a_on = !(a.debug & 2); sch.b_on = !(a.debug & 1);
     const bool nowait = (a.debug & 7) != 0;
-    const long long total = (a.nbatch << LOG_TPT) * (sch.a_on + sch.b_on);
+    const long long total = a.nbatch * (((long long)sch.a_on << LOG_TPT) + (long long)sch.b_on * TPB);
     const int first = blockIdx.x, stride = gridDim.x;
     const int my_tiles = first < total ? (int)((total - first + stride - 1) / stride) : 0;
 
@@ -363,13 +390,14 @@ fft_fused_kernel(const FusedArgs a, const __grid_constant__ CUtensorMap tm_in, c
         FusedItem it = cur.locate(sch, first + (long long)w * stride);
         // issue the four quarter loads of tile `x` into the buffer; WAITQ: quarter q only after the store of quarter q has been read
         auto load = [&](const FusedItem& x, auto waitq) {
-            const int blk = (int)(x.tau & ((1 << LOG_TPT) - 1));
-            const long long trg = x.tau >> LOG_TPT;
+            const bool half_b = HERM && x.is_b;   // pass-B tiles of a real transform are numbered 0 .. TPB - 1 per transform
+            const int blk = half_b ? (int)(x.tau % TPB) : (int)(x.tau & ((1 << LOG_TPT) - 1));
+            const long long trg = half_b ? x.tau / TPB : x.tau >> LOG_TPT;
             kinds[4 * w] = x.is_b; kinds[4 * w + 1] = blk; kinds[4 * w + 2] = x.g; kinds[4 * w + 3] = (int)trg;
             mbar_expect_tx(&full[w], (R2C && !x.is_b) ? PIPE_TILE * (uint32_t)sizeof(double) : PIPE_TILE * (uint32_t)sizeof(cd));
             if (x.is_b) {
                 asm volatile("fence.proxy.async;" ::: "memory");
-                const cd* src = a.scratch + (((size_t)(x.g % a.slots) * a.gt) << LOGN) + (size_t)x.tau * PIPE_TILE;
+                const cd* src = a.scratch + ((((size_t)(x.g % a.slots) * a.gt) + (size_t)trg) << LOGN) + (size_t)blk * PIPE_TILE;
 #pragma unroll
                 for (int q = 0; q < 4; q++) {
                     waitq(q);
@@ -396,7 +424,7 @@ fft_fused_kernel(const FusedArgs a, const __grid_constant__ CUtensorMap tm_in, c
             else if (q == 2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
             else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
         };
-        if (it.is_b && !nowait) wait_count(a.flags + it.g, (int)sch.tiles_of(it.g));
+        if (it.is_b && !nowait) wait_count(a.flags + it.g, (int)sch.tiles_of(it.g));   // every pass-A tile of the group has been stored
         load(it, nowaitq);
 #ifdef FUSED_PROF
         long long mp[6] = {0, 0, 0, 0, 0, 0};   // load latency, load->staged, store read-out (incl. chase), publish, tiles
@@ -421,7 +449,7 @@ fft_fused_kernel(const FusedArgs a, const __grid_constant__ CUtensorMap tm_in, c
             if (!cur_it.is_b && cur_it.g >= a.slots && !nowait) {
                 // the scratch slot of this group was last read by pass B of group g - slots
                 war_p = a.flags + a.ngroups + (cur_it.g - a.slots);
-                war_need = (int)sch.tiles_of(cur_it.g - a.slots);
+                war_need = (int)sch.tiles_b(cur_it.g - a.slots);
                 war_seen = ld_acquire_gpu(war_p);
             }
             // ---- store, one bulk group per quarter ----
@@ -431,24 +459,44 @@ fft_fused_kernel(const FusedArgs a, const __grid_constant__ CUtensorMap tm_in, c
             mp[1] += m2 - m1;
 #endif
             {
-                const int blk = (int)(cur_it.tau & ((1 << LOG_TPT) - 1));
-                const long long trg = cur_it.tau >> LOG_TPT;
+                const bool half_b = HERM && cur_it.is_b;
+                const int blk = half_b ? (int)(cur_it.tau % TPB) : (int)(cur_it.tau & ((1 << LOG_TPT) - 1));
+                const long long trg = half_b ? cur_it.tau / TPB : cur_it.tau >> LOG_TPT;
                 if (!cur_it.is_b) {
                     if (war_seen < war_need) wait_count(war_p, war_need);
                     const long long trl = (long long)(cur_it.g % a.slots) * a.gt + trg;
 #pragma unroll
                     for (int q = 0; q < 4; q++) {
                         if constexpr (COLS) tma_store_4d(&tm_sc, 0, blk, q * 64, (int)trl, buf + q * QT, pol_last);   // [slot][k_hi][t_lo][c16]
-                        else tma_store_2d(&tm_sc, 2 * (blk << LC), (int)((trl << LM) + q * (QT >> LC)), buf + q * QT, pol_last);
+                        else if constexpr (HERM) {
+                            // rows k < M/2 (two quarters) and the row k = M/2 (C contiguous elements of scratch[c + R k]); the rest is never read
+                            if (q < 2) tma_store_2d(&tm_sc, 2 * (blk << LC), (int)((trl << LM) + q * (QT >> LC)), buf + q * QT, pol_last);
+                            else if (q == 2)
+                                bulk_store_hint(const_cast<cd*>(a.scratch) + ((size_t)trl << LOGN) + ((size_t)1 << (LOGN - 1)) + ((size_t)blk << LC), buf + 2 * QT,
+                                                (uint32_t)sizeof(cd) << LC, pol_last);
+                        } else tma_store_2d(&tm_sc, 2 * (blk << LC), (int)((trl << LM) + q * (QT >> LC)), buf + q * QT, pol_last);
                         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                     }
                 } else if constexpr (!BDIRECT) {
                     const long long tr = (long long)cur_it.g * a.gt + trg;
 #pragma unroll
                     for (int q = 0; q < 4; q++) {
-                        if constexpr (R2C) {   // rows q < R/2 (bins below n/2) are the first two quarters; then the Nyquist bin X[M R/2]
+                        if constexpr (R2C && !HERM) {   // rows q < R/2 (bins below n/2) are the first two quarters; then the Nyquist bin X[M R/2]
                             if (q < 2) tma_store_3d(&tm_out, 2 * (blk << LC2), q * (QT >> LC2), (int)tr, buf + q * QT, pol_first);
                             else if (q == 2 && blk == 0) bulk_store(a.out + (size_t)tr * ((1 << (LOGN - 1)) + 1) + (1 << (LOGN - 1)), buf + 2 * QT, sizeof(cd));
+                        } else if constexpr (HERM) {
+                            // quarters 0, 1: the bins k + M q, q < R/2, of the tile's columns; quarters 2, 3: the mirrored rows, conj(X[k + M q]) for
+                            // q >= R/2 staged as [R - 1 - q][C2 - 1 - (k - k0)] = the bins of the columns M - k0 - C2 + 1 .. M - k0 (column M of the
+                            // first tile - the mirror of k = 0, which that tile produces directly - falls off the tensor and is dropped).
+                            // The last tile (k0 = M/2) holds one valid column: its direct half goes through the map that ends at column M/2.
+                            if (blk == TPB - 1) {
+                                if (q < 2) tma_store_3d(&tm_out2, 2 * (blk << LC2), q * (QT >> LC2), (int)tr, buf + q * QT, pol_first);
+                            } else {
+                                if (q < 2) tma_store_3d(&tm_out, 2 * (blk << LC2), q * (QT >> LC2), (int)tr, buf + q * QT, pol_first);
+                                else tma_store_3d(&tm_out, 2 * ((1 << LM) - (blk << LC2) - (1 << LC2) + 1), (q - 2) * (QT >> LC2), (int)tr, buf + q * QT, pol_first);
+                                // the Nyquist bin X[M R/2] (k = 0, q = R/2) sits at the end of the mirrored block of the first tile
+                                if (q == 3 && blk == 0) bulk_store(a.out + (size_t)tr * ((1 << (LOGN - 1)) + 1) + (1 << (LOGN - 1)), buf + PIPE_TILE - 1, sizeof(cd));
+                            }
                         } else if constexpr (C2R) {   // real rows: a quarter is 1024 doubles
                             tma_store_2d(&tm_out, blk << LC2, (int)((tr << LR) + q * (QT >> LC2)), reinterpret_cast<double*>(buf) + q * QT, pol_first);
                         } else if constexpr (COLS)   // [b][q][k_hi][c]
@@ -496,7 +544,7 @@ fft_fused_kernel(const FusedArgs a, const __grid_constant__ CUtensorMap tm_in, c
     const double sc = a.scale;
     int b = g2, n = 0;   // ring buffer and use count of tile k = g2, g2 + 2, ... (b = k % 3, n = k / 3)
 #ifdef FUSED_PROF
-    long long pr_e = 0, pr_f = 0;
+    long long pr_e = 0, pr_f = 0, pr_busy[2] = {0, 0}, pr_cnt[2] = {0, 0};
     const long long pr_t0 = clock64();
 #endif
     for (int k = g2; k < my_tiles; k += 2) {
@@ -582,7 +630,9 @@ fft_fused_kernel(const FusedArgs a, const __grid_constant__ CUtensorMap tm_in, c
             if constexpr (COLS) {
                 // the tile is [t_lo][c16], the geometry of a pass-A tile; stages 9 .. 16 with T[8 + s][kb + 256 q]
                 typedef Geo<4, 8, 0, 0, 4, false> G0;
+                typedef Geo<4, 8, 0, 4, 4, false> G1;
                 const G0 g0(t);
+                const G1 g1(t);
                 fused_gather<G0, SwzId, 4, false>(x, sm, g0);
                 {
                     cd tw[16];
@@ -591,8 +641,6 @@ fft_fused_kernel(const FusedArgs a, const __grid_constant__ CUtensorMap tm_in, c
                 }
                 fused_scatter<G0, SwzId, 4>(x, sm, g0);   // in place per thread
                 group_sync(g2);
-                typedef Geo<4, 8, 0, 4, 4, false> G1;
-                const G1 g1(t);
                 fused_gather<G1, SwzId, 4, false>(x, sm, g1);
                 {
                     cd tw[16];
@@ -614,6 +662,11 @@ fft_fused_kernel(const FusedArgs a, const __grid_constant__ CUtensorMap tm_in, c
             }
             typedef typename SwzBlast<LR>::type SWL;
             typedef typename std::conditional<B3, SwzId, SWL>::type SW1;   // layout after sub-pass 0
+            constexpr int AL = LR - 4;   // stages of this pass done before the last sub-pass
+            typedef Geo<0, LR, LC2, RB0, 4, false> G1;    // middle sub-pass (three sub-passes only)
+            typedef Geo<0, LR, LC2, AL, 4, true> GL;      // last sub-pass
+            const G1 g1(t);
+            const GL gl(t);
             {
                 typedef Geo<0, LR, LC2, 0, RB0, false> G0;
                 constexpr int NB = 16 >> RB0, R0 = 1 << RB0;
@@ -638,8 +691,6 @@ fft_fused_kernel(const FusedArgs a, const __grid_constant__ CUtensorMap tm_in, c
             }
             group_sync(g2);
             if constexpr (B3) {
-                typedef Geo<0, LR, LC2, RB0, 4, false> G1;
-                const G1 g1(t);
                 fused_gather<G1, SW1, 4, false>(x, sm, g1);
                 {
                     cd tw[16];
@@ -650,9 +701,6 @@ fft_fused_kernel(const FusedArgs a, const __grid_constant__ CUtensorMap tm_in, c
                 fused_scatter<G1, SWL, 4>(x, sm, g1);
                 group_sync(g2);
             }
-            constexpr int AL = LR - 4;   // stages of this pass done before the last sub-pass
-            typedef Geo<0, LR, LC2, AL, 4, true> GL;
-            const GL gl(t);
             fused_gather<GL, SWL, 4, false>(x, sm, gl);
             if constexpr (BDIRECT) fused_stage_done(&staged[b], t);   // this warp has read its part: the buffer goes back when all have
             {
@@ -677,6 +725,14 @@ fft_fused_kernel(const FusedArgs a, const __grid_constant__ CUtensorMap tm_in, c
                     double* p = reinterpret_cast<double*>(sm) + gl.hi + (gl.kloc << LC2);
 #pragma unroll
                     for (int q = 0; q < 16; q++) p[q << (AL + LC2)] = x[q].x * sc;
+                } else if constexpr (HERM) {
+                    // q' < 8 (q < R/2): [q][k] as ever; q' >= 8: the conjugate at [R - 1 - q][C2 - 1 - k] of the second half of the buffer
+                    cd* p = sm + gl.hi + (gl.kloc << LC2);
+                    cd* pm = sm + PIPE_TILE / 2 + (((1 << LR) - 1 - gl.kloc) << LC2) + ((1 << LC2) - 1 - gl.hi);
+#pragma unroll
+                    for (int q = 0; q < 8; q++) p[q << (AL + LC2)] = x[q];
+#pragma unroll
+                    for (int q = 8; q < 16; q++) pm[-(q << (AL + LC2))] = make_double2(x[q].x, -x[q].y);
                 } else {
                     cd* p = sm + gl.hi + (gl.kloc << LC2);
 #pragma unroll
@@ -689,6 +745,9 @@ fft_fused_kernel(const FusedArgs a, const __grid_constant__ CUtensorMap tm_in, c
                 fused_stage_done(&staged[b], t);
             }
         }
+#ifdef FUSED_PROF
+        pr_busy[is_b] += clock64() - c2; pr_cnt[is_b]++;
+#endif
         b += 2;
         if (b >= PIPE_STAGES) { b -= PIPE_STAGES; n++; }
     }
@@ -696,6 +755,8 @@ fft_fused_kernel(const FusedArgs a, const __grid_constant__ CUtensorMap tm_in, c
     if (t == 0 && a.prof) {
         long long* q = a.prof + (blockIdx.x * 2 + g2) * 4;
         q[0] = pr_e; q[1] = pr_f; q[2] = clock64() - pr_t0; q[3] = (my_tiles - g2 + 1) / 2;
+        long long* q2 = a.prof + 12 * 1024 + (blockIdx.x * 2 + g2) * 4;
+        q2[0] = pr_busy[0]; q2[1] = pr_cnt[0]; q2[2] = pr_busy[1]; q2[3] = pr_cnt[1];
     }
 #endif
 }
@@ -713,10 +774,10 @@ inline const void* fused_func(int lm, int lr, int inverse) {
     return f;
 }
 const void* fused_cols_func(int inverse);   // column mode (fft_kernels_fused1.cu)
-const void* fused_r2c_func_0(int lm, int lr);
-const void* fused_r2c_func_1(int lm, int lr);
-const void* fused_r2c_func_2(int lm, int lr);
-const void* fused_r2c_func_3(int lm, int lr);
+const void* fused_r2c_func_0(int lm, int lr, int herm);
+const void* fused_r2c_func_1(int lm, int lr, int herm);
+const void* fused_r2c_func_2(int lm, int lr, int herm);
+const void* fused_r2c_func_3(int lm, int lr, int herm);
 const void* fused_c2r_func_0(int lm, int lr);
 const void* fused_c2r_func_1(int lm, int lr);
 const void* fused_c2r_func_2(int lm, int lr);
@@ -728,15 +789,16 @@ inline const void* fused_c2r_func(int lm, int lr) {
     if (!f) f = fused_c2r_func_3(lm, lr);
     return f;
 }
-inline const void* fused_r2c_func(int lm, int lr) {
-    const void* f = fused_r2c_func_0(lm, lr);
-    if (!f) f = fused_r2c_func_1(lm, lr);
-    if (!f) f = fused_r2c_func_2(lm, lr);
-    if (!f) f = fused_r2c_func_3(lm, lr);
+inline const void* fused_r2c_func(int lm, int lr, int herm) {
+    const void* f = fused_r2c_func_0(lm, lr, herm);
+    if (!f) f = fused_r2c_func_1(lm, lr, herm);
+    if (!f) f = fused_r2c_func_2(lm, lr, herm);
+    if (!f) f = fused_r2c_func_3(lm, lr, herm);
     return f;
 }
 
-// tm[0..2]: tensor maps of the input (pass-A loads), the scratch ring (pass-A stores) and the output (pass-B stores).
+// tm[0..3]: tensor maps of the input (pass-A loads), the scratch ring (pass-A stores), the output (pass-B stores) and - r2c
+// only, a copy of tm[2] elsewhere - the output cut off after column M/2 (the single valid column of the last pass-B tile).
 // The CTAs synchronise through global counters, so all of them must be resident: a cooperative launch makes the
 // driver guarantee that (or fail) even when other kernels compete for the SMs.
 inline cudaError_t launch_fused(const void* func, const FusedArgs& a, const CUtensorMap* tm, int grid, cudaStream_t s) {
@@ -746,7 +808,7 @@ inline cudaError_t launch_fused(const void* func, const FusedArgs& a, const CUte
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeCooperative; at[0].val.cooperative = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
-    void* args[4] = {(void*)&a, (void*)&tm[0], (void*)&tm[1], (void*)&tm[2]};
+    void* args[5] = {(void*)&a, (void*)&tm[0], (void*)&tm[1], (void*)&tm[2], (void*)&tm[3]};
     return cudaLaunchKernelExC(&cfg, func, args);
 }
 

@@ -249,7 +249,8 @@ extern "C" int fftb200_pointwise_mul(void* y, const void* a, const void* b, size
 // ---------------------------------------------------------------------------------------------
 enum { BUF_IN = 0, BUF_OUT = 1, BUF_SCRATCH = 2 };
 
-enum { ACC_N = 8192 };  // accurate tables cover stages m <= 8192 (hybrid twiddles)
+enum { ACC_N = 8192 };
+enum { R2C_HERM_MAX_LOG = 16 };   // largest r2c size on the Hermitian schedule: mismatch vs the oracle 3.4e-13 there, 7.9e-13 at 2^17, 1.8e-12 at 2^18 (profiles/r02_real.md)  // accurate tables cover stages m <= 8192 (hybrid twiddles)
 
 struct Pass {
     const KernelInfo* k;   // nullptr: persistent TMA kernel fft_pipe_kernel<log_p>, or the fused kernel when fused_lm > 0
@@ -291,6 +292,7 @@ struct fftb200_plan {
     int peer_lw = 0, peer_lrows = 0, peer_lg = 0, peer_me = 0;
     double scale = 0.0;        // 1/m, or the caller's value for partial plans of a distributed transform
     cd* work = nullptr;        // Bluestein / R2C: padded complex work array, m * batch
+    bool r2c_herm = false;     // R2C of 2^14 .. : the fused kernel transforms only the columns k <= M/2 in pass B (fft_fused.cuh, HERM)
     bool fused_c2r = false;    // C2R of 2^14 .. 2^20 points: the fused kernel stores the real parts itself
     bool pipe_blue = false;    // Bluestein with m = 512 .. 4096: both transforms in the pipe kernel's Bluestein variants, no elementwise kernels
     bool pipe_real = false;    // R2C / C2R of 512 .. 4096 points: the pipe kernel reads reals / half spectra itself (no work array)
@@ -536,6 +538,8 @@ static int enqueue_fused(fftb200_plan* p, const Pass& ps, const cd* in, cd* out,
         p->fscratch = (cd*)fftb200_malloc(sizeof(cd) * need);
         if (!p->fscratch) return -1;
         p->fscratch_elems = need;
+        // r2c: the last pass-B tile of a transform reads rows above k = M/2 that pass A never stores (their results are dropped)
+        CU(cudaMemsetAsync(p->fscratch, 0, sizeof(cd) * need, p->stream));
     }
     const size_t nflags = (size_t)(2 * G + 1);
     if (p->fflags_count < nflags) {
@@ -549,7 +553,8 @@ static int enqueue_fused(fftb200_plan* p, const Pass& ps, const cd* in, cd* out,
     // box C x M/4; the scratch ring the same way over slots * gt transforms; the output as [nbatch * R][M], box C2 x R/4
     EncodeTiledFn enc = encode_tiled_fn();
     if (!enc) return fail("cuTensorMapEncodeTiled is not available from this driver");
-    CUtensorMap tm[3];
+    CUtensorMap tm[4];
+    memset(tm, 0, sizeof(tm));
     int promo = 12 - lm >= 4 ? 2 : 12 - lm >= 3 ? 1 : 0;      // rows of 256 / 128 / 64 bytes
     if (const char* e = getenv("FFTB200_FUSED_PROMO")) promo = atoi(e);
     const CUtensorMapL2promotion pr = promo >= 2 ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B : promo == 1 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B
@@ -569,6 +574,11 @@ static int enqueue_fused(fftb200_plan* p, const Pass& ps, const cd* in, cd* out,
         r = enc(&tm[2], CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, (void*)out, odim, ostr, obox, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                 CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled failed (%d) for the half spectrum", (int)r);
+        // the same array cut off after column M/2: the last pass-B tile of a real transform holds one valid column (fft_fused.cuh, R2C)
+        const cuuint64_t odim2[3] = {((cuuint64_t)1 << lm) + 2, (cuuint64_t)1 << (lr - 1), (cuuint64_t)nbatch};
+        r = enc(&tm[3], CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, (void*)out, odim2, ostr, obox, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled failed (%d) for the cut-off half spectrum", (int)r);
     }
     for (int i = 0; i < 3 && !cols; i++) {
         if (r2c == 1 && i != 1) continue;
@@ -618,9 +628,11 @@ static int enqueue_fused(fftb200_plan* p, const Pass& ps, const cd* in, cd* out,
     if (!d_prof) d_prof = (long long*)fftb200_malloc(sizeof(long long) * 16 * 1024);
     fa.prof = d_prof;
 #endif
-    const long long items = 2 * nbatch * tpt;
+    if (r2c != 1) tm[3] = tm[2];
+    const bool herm = r2c == 1 && p->r2c_herm;
+    const long long items = herm ? nbatch * (tpt + tpt / 2 + 1) : 2 * nbatch * tpt;   // Hermitian schedule: pass B on the columns k <= M/2 only
     const int grid = (int)(items < ps.grid_max ? items : ps.grid_max);
-    const void* func = r2c == 1 ? fused_r2c_func(lm, lr) : r2c == 2 ? fused_c2r_func(lm, lr) : cols ? fused_cols_func(inverse) : fused_func(lm, lr, inverse);
+    const void* func = r2c == 1 ? fused_r2c_func(lm, lr, herm) : r2c == 2 ? fused_c2r_func(lm, lr) : cols ? fused_cols_func(inverse) : fused_func(lm, lr, inverse);
     if (!func) return fail("no fused kernel for 2^%d x 2^%d", lm, lr);
     CU(launch_fused(func, fa, tm, grid, p->stream));
 #ifdef FUSED_PROF
@@ -640,6 +652,13 @@ static int enqueue_fused(fftb200_plan* p, const Pass& ps, const cd* in, cd* out,
         }
         fprintf(stderr, "fused prof: per group-tile cycles: total %.0f, staged-wait %.0f, full-wait %.0f, busy %.0f (tiles/group %.1f)\n",
                 tot / tiles, e / tiles, f / tiles, (tot - e - f) / tiles, tiles / (2 * grid));
+        {
+            std::vector<long long> hb(8 * grid);
+            CU(cudaMemcpy(hb.data(), fa.prof + 12 * 1024, sizeof(long long) * 8 * grid, cudaMemcpyDeviceToHost));
+            double ba = 0, ca = 0, bb = 0, cb = 0;
+            for (int i = 0; i < 2 * grid; i++) { ba += hb[i * 4]; ca += hb[i * 4 + 1]; bb += hb[i * 4 + 2]; cb += hb[i * 4 + 3]; }
+            fprintf(stderr, "fused prof: busy cycles per tile: pass A %.0f (%.0f tiles), pass B %.0f (%.0f tiles)\n", ca ? ba / ca : 0, ca, cb ? bb / cb : 0, cb);
+        }
     }
 #endif
     return 0;
@@ -829,12 +848,17 @@ extern "C" int fftb200_plan_create(fftb200_plan** out, const fftb200_plan_desc* 
         }
         if (d->kind == FFTB200_R2C) {
             const bool fused_r2c = p->passes.size() == 1 && p->passes[0].fused_lm && !getenv("FFTB200_NO_FUSED_R2C") &&
-                                   fused_r2c_func(p->passes[0].fused_lm, p->passes[0].fused_lr);
+                                   fused_r2c_func(p->passes[0].fused_lm, p->passes[0].fused_lr, 0);
             if (fused_r2c) {
-                // promotion and extraction happen inside the fused kernel (fft_fused.cuh, R2C)
-                if (cudaFuncSetAttribute(fused_r2c_func(p->passes[0].fused_lm, p->passes[0].fused_lr), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                // promotion and extraction happen inside the fused kernel (fft_fused.cuh, R2C). Up to R2C_HERM_MAX_LOG points pass B runs on
+                // the columns k <= M/2 only and writes the other half of the bins as conjugates; above, the conjugate of the reference's
+                // X[j] is no longer within 1e-12 of ITS X[N - j] (its twiddle recurrence is not conjugate-symmetric), so every column is transformed.
+                p->r2c_herm = p->log_n <= R2C_HERM_MAX_LOG;
+                if (const char* e = getenv("FFTB200_R2C_HERMITIAN")) p->r2c_herm = atoi(e) != 0;
+                if (cudaFuncSetAttribute(fused_r2c_func(p->passes[0].fused_lm, p->passes[0].fused_lr, p->r2c_herm), cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)FUSED_SMEM) != cudaSuccess) { rc = fail("cudaFuncSetAttribute failed"); break; }
-                p->desc += " [real in, half spectrum out, no promote / extract passes]";
+                p->desc += p->r2c_herm ? " [real in, half spectrum out, no promote / extract passes, pass B on the columns k <= M/2]"
+                                       : " [real in, half spectrum out, no promote / extract passes]";
             } else if (p->passes.size() == 1 && !p->passes[0].k && p->passes[0].log_p <= 12 && !getenv("FFTB200_NO_PIPE_REAL")) {
                 if (cudaFuncSetAttribute(pipe_real_func(p->passes[0].log_p, PIPE_R2C), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PIPE_SMEM) != cudaSuccess) { rc = fail("cudaFuncSetAttribute failed"); break; }
                 p->pipe_real = true;

@@ -97,10 +97,8 @@ class CudaBackend:
         cur = self.torch.cuda.current_stream()
         if before:
             self.s_head.wait_stream(cur)
-            for t in tensors:
-                t.record_stream(self.s_head)
         else:
-            cur.wait_stream(self.s_head)
+            cur.wait_stream(self.s_head)   # also orders any later free / reuse of x and out on the caller's stream
 
     def permute_bac(self, dst, src, A, B, Cc):
         if self.F.lib.fftb200_permute_bac(dst.data_ptr(), src.data_ptr(), A, B, Cc, self.s_head.cuda_stream) != 0:
@@ -248,11 +246,11 @@ class DistFFTP2P:
         t, L = self.torch, self.F.lib
         cur = t.cuda.current_stream()
         self.s.wait_stream(cur)            # x was produced on the caller's stream
-        x.record_stream(self.s)
         out = C.c_void_p()
         if L.fftb200_dist_exec_async(self.h, x.data_ptr(), C.byref(out)) != 0:
             raise RuntimeError("fftb200_dist_exec_async: " + L.fftb200_last_error().decode())
-        cur.wait_stream(self.s)            # the result is ordered before whatever the caller enqueues next
+        cur.wait_stream(self.s)            # the result (and the last read of x) is ordered before whatever the caller enqueues next,
+                                           # so x needs no record_stream (which would outlive the plan's stream and fail at free time)
         return _DevView(out.value, self.nloc).tensor()
 
     def close(self):

@@ -233,3 +233,49 @@ def test_plan_follows_its_device(gpu, port, O):
     assert O.rel_l2(out, port.fft_batch(x, -1)) <= TOL
     L.fft_gpu_destroy_plan(plan)
     L.fft_gpu_free(m)
+
+
+@pytest.mark.parametrize("n,batch", [(1 << 13, 33), (1 << 14, 1), (1 << 14, 77), (1 << 15, 40), (1 << 16, 9), (1 << 17, 5), (1 << 18, 3), (1 << 19, 2),
+                                     (1 << 20, 3)])
+def test_hermitian_r2c_in_the_fused_kernel(gpu, port, O, n, batch, monkeypatch):
+    """r2c of 2^14 .. 2^16 points: pass B of the fused kernel transforms only the columns k <= M/2 and writes the bins of the columns
+    M - k as conjugates (fft_fused.cuh, HERM). FFTB200_NO_FUSED_R2C=1 is the promote -> full c2c -> extract plan: the
+    directly computed bins (j mod M <= M/2) are the same arithmetic, bit for bit; the mirrored ones are conj X[j] where the reference has
+    its own X[N - j] - equal only to the accuracy of its twiddle recurrence, which is why sizes above 2^16 keep the full pass B (measured
+    mismatch 7.9e-13 at 2^17, 1.8e-12 at 2^18, 7e-12 at 2^20: profiles/r02_real.md). Every size against the oracle at the 1e-12 bar."""
+    import torch
+    L = gpu.lib
+    x = port.fill(81, 0, n * batch).real.copy().reshape(batch, n)
+    xd = torch.from_numpy(x).cuda()
+
+    def run():
+        plan = gpu.engine_plan(n, batch, gpu.FFTB200_R2C)
+        desc = L.fftb200_plan_describe(plan).decode()
+        yd = torch.full((batch, n // 2 + 1), float("nan"), dtype=torch.complex128, device="cuda")
+        for _ in range(2):
+            assert L.fftb200_plan_exec(plan, xd.data_ptr(), yd.data_ptr()) == 0, L.fftb200_last_error()
+        L.fftb200_plan_destroy(plan)
+        return yd.cpu().numpy(), desc
+    y1, d1 = run()
+    herm = (1 << 14) <= n <= (1 << 16)
+    assert ("columns k <= M/2" in d1) == herm, d1
+    assert np.isfinite(y1.view(np.float64)).all(), "a bin was not written"
+    monkeypatch.setenv("FFTB200_NO_FUSED_R2C", "1")
+    y2, d2 = run()
+    monkeypatch.delenv("FFTB200_NO_FUSED_R2C")
+    assert "no promote" not in d2 or n <= 8192
+    if herm:
+        lm = (int(np.log2(n)) + 1) // 2
+        k = np.arange(n // 2 + 1) % (1 << lm)
+        direct = k <= (1 << lm) // 2
+        assert np.array_equal(y1[:, direct], y2[:, direct])
+        assert O.rel_l2(y1, y2) <= 5e-13
+        # forcing the schedule off gives the full pass B: identical to the promoted path everywhere
+        monkeypatch.setenv("FFTB200_R2C_HERMITIAN", "0")
+        y3, d3 = run()
+        monkeypatch.delenv("FFTB200_R2C_HERMITIAN")
+        assert "columns k <= M/2" not in d3 and np.array_equal(y3, y2)
+    elif n > (1 << 16):
+        assert np.array_equal(y1, y2)
+    rows = sorted({0, batch - 1})
+    assert O.rel_l2(y1[rows], np.stack([port.r2c(x[r]) for r in rows])) <= TOL
