@@ -120,6 +120,7 @@ _SIGS = {
     "fftb200_barrier_enqueue": (C.c_int, [_vp, _vp]),
     "fftb200_barrier_destroy": (None, [_vp]),
     "fftb200_stream_sync": (C.c_int, [_vp]),
+    "fftb200_enable_peer_access": (C.c_int, [C.c_int]),
     # include/fftb200_dist.h (argtypes with the callback are set by dist.py)
     "fftb200_dist_choose_split": (C.c_int, [C.c_int, C.c_int]),
     "fftb200_dist_sync": (C.c_int, [_vp]),

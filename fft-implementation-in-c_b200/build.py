@@ -83,7 +83,7 @@ def build_programs(force=False):
         src, exe = os.path.join(src_dir, f), os.path.join(bin_dir, f[:-2])
         if force or _newer([src, LIB], exe):
             r = subprocess.run([GCC, "-std=c99", "-O2", "-Wall", "-Wextra", "-I" + os.path.join(ROOT, "include"), src, "-o", exe,
-                                "-L" + os.path.dirname(LIB), "-lfft_b200", "-Wl,-rpath,$ORIGIN/../lib", "-lm"],
+                                "-L" + os.path.dirname(LIB), "-lfft_b200", "-Wl,-rpath,$ORIGIN/../lib", "-lm", "-lpthread"],
                                capture_output=True, text=True)
             if r.returncode != 0:
                 raise RuntimeError("build failed: " + f + "\n" + r.stderr)

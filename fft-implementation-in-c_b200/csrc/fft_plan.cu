@@ -249,8 +249,9 @@ extern "C" int fftb200_pointwise_mul(void* y, const void* a, const void* b, size
 // ---------------------------------------------------------------------------------------------
 enum { BUF_IN = 0, BUF_OUT = 1, BUF_SCRATCH = 2 };
 
-enum { ACC_N = 8192 };
-enum { R2C_HERM_MAX_LOG = 16 };   // largest r2c size on the Hermitian schedule: mismatch vs the oracle 3.4e-13 there, 7.9e-13 at 2^17, 1.8e-12 at 2^18 (profiles/r02_real.md)  // accurate tables cover stages m <= 8192 (hybrid twiddles)
+enum { ACC_N = 8192 };  // accurate tables cover stages m <= 8192 (hybrid twiddles)
+// largest r2c size on the Hermitian schedule: mismatch vs the oracle 3.4e-13 there, 7.9e-13 at 2^17, 1.8e-12 at 2^18 (profiles/r02_real.md)
+enum { R2C_HERM_MAX_LOG = 16 };
 
 struct Pass {
     const KernelInfo* k;   // nullptr: persistent TMA kernel fft_pipe_kernel<log_p>, or the fused kernel when fused_lm > 0
@@ -292,6 +293,7 @@ struct fftb200_plan {
     int peer_lw = 0, peer_lrows = 0, peer_lg = 0, peer_me = 0;
     double scale = 0.0;        // 1/m, or the caller's value for partial plans of a distributed transform
     cd* work = nullptr;        // Bluestein / R2C: padded complex work array, m * batch
+    fftb200_plan* child = nullptr;   // R2C of a non-power-of-two length: the Bluestein c2c plan that transforms the promoted input
     bool r2c_herm = false;     // R2C of 2^14 .. : the fused kernel transforms only the columns k <= M/2 in pass B (fft_fused.cuh, HERM)
     bool fused_c2r = false;    // C2R of 2^14 .. 2^20 points: the fused kernel stores the real parts itself
     bool pipe_blue = false;    // Bluestein with m = 512 .. 4096: both transforms in the pipe kernel's Bluestein variants, no elementwise kernels
@@ -809,6 +811,26 @@ extern "C" int fftb200_plan_create(fftb200_plan** out, const fftb200_plan_desc* 
     do {
         if (d->kind == FFTB200_C2C || d->kind == FFTB200_R2C || d->kind == FFTB200_C2R) {
             if (d->kind == FFTB200_C2R && d->direction != 1) { rc = fail("plan_create: a c2r plan is an inverse transform (direction +1)"); break; }
+            if (!pow2 && d->kind == FFTB200_R2C && d->direction == -1) {
+                // real input of any length (the reference plans it: fft_auto.c:391-403 promotes and routes non-powers of two to
+                // Bluestein, :136-172): promote on the device, Bluestein c2c of length n, bins 0 .. n/2
+                if (!d->chirp) { rc = fail("plan_create: r2c of a non-power-of-two length needs the host chirp table"); break; }
+                fftb200_plan_desc cdsc = *d;
+                cdsc.kind = FFTB200_BLUESTEIN;
+                if (fftb200_plan_create(&p->child, &cdsc) != 0) { rc = -1; break; }
+                p->work = (cd*)fftb200_malloc(sizeof(cd) * (size_t)d->n * (size_t)d->batch);
+                if (!p->work) { rc = -1; break; }
+                if (cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking) != cudaSuccess ||
+                    cudaStreamCreateWithFlags(&p->s_up, cudaStreamNonBlocking) != cudaSuccess ||
+                    cudaStreamCreateWithFlags(&p->s_down, cudaStreamNonBlocking) != cudaSuccess ||
+                    cudaEventCreate(&p->ev0) != cudaSuccess || cudaEventCreate(&p->ev1) != cudaSuccess) { rc = fail("cudaStreamCreate failed"); break; }
+                if (fftb200_plan_set_stream(p->child, p->stream) != 0) { rc = -1; break; }
+                p->m = d->n; p->log_n = 0;
+                p->launches = p->child->launches + 2;
+                p->desc = "r2c n=" + std::to_string(d->n) + " b=" + std::to_string(d->batch) + ": promote + [" + p->child->desc + "] + bins 0 .. n/2";
+                *out = p;
+                return 0;
+            }
             if (!pow2) { rc = fail("plan_create: kind %d needs a power-of-two n (got %d)", d->kind, d->n); break; }
             p->m = d->n;
         } else if (d->kind == FFTB200_BLUESTEIN) {
@@ -1147,6 +1169,19 @@ extern "C" void* fftb200_ipc_open(const void* handle64) {
     if (e != cudaSuccess) { fail("cudaIpcOpenMemHandle: %s", cudaGetErrorString(e)); cudaGetLastError(); return nullptr; }
     return p;
 }
+// Ranks that are threads of one process reach each other's buffers directly: enable peer access from the current device.
+extern "C" int fftb200_enable_peer_access(int peer_device) {
+    int cur = -1;
+    CU(cudaGetDevice(&cur));
+    if (cur == peer_device) return 0;
+    int can = 0;
+    CU(cudaDeviceCanAccessPeer(&can, cur, peer_device));
+    if (!can) return fail("device %d cannot access device %d", cur, peer_device);
+    const cudaError_t e = cudaDeviceEnablePeerAccess(peer_device, 0);
+    if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return fail("cudaDeviceEnablePeerAccess(%d): %s", peer_device, cudaGetErrorString(e));
+    cudaGetLastError();
+    return 0;
+}
 extern "C" int fftb200_ipc_close(void* p) {
     if (p) CU(cudaIpcCloseMemHandle(p));
     return 0;
@@ -1162,6 +1197,15 @@ static int exec_range(fftb200_plan* p, const void* d_in, void* d_out, long long 
     const int inverse = p->dir > 0;
     if (p->kind == FFTB200_C2C) return enqueue_c2c(p, (const cd*)d_in, (cd*)d_out, inverse, nbatch);
     const size_t m = (size_t)p->m, n = (size_t)p->n, total = m * (size_t)nbatch;
+    if (p->child) {   // r2c of a non-power-of-two length
+        if (nbatch <= 0) return 0;
+        const size_t nh = n / 2 + 1, tot_in = n * (size_t)nbatch, tot_out = nh * (size_t)nbatch;
+        r2c_promote_kernel<<<grid_for(tot_in), 256, 0, p->stream>>>(p->work, (const double*)d_in, tot_in);
+        if (exec_range(p->child, p->work, p->work, nbatch) != 0) return -1;
+        r2c_extract_kernel<<<grid_for(tot_out), 256, 0, p->stream>>>((cd*)d_out, p->work, n, nh, tot_out);
+        CU(cudaGetLastError());
+        return 0;
+    }
     if ((p->kind == FFTB200_R2C || p->kind == FFTB200_C2R) && (p->pipe_real || (p->kind == FFTB200_R2C && !p->work)) && nbatch > 0) {
         // the single-kernel real transforms read packed rows that other CTAs' outputs would overwrite: out of place only
         const size_t half = sizeof(cd) * (n / 2 + 1), full = sizeof(double) * n;
@@ -1362,6 +1406,7 @@ extern "C" void fftb200_plan_destroy(fftb200_plan* p) {
     DeviceGuard dg(p->device);
     if (p->stream) cudaStreamSynchronize(p->stream);
     if (p->s_down) cudaStreamSynchronize(p->s_down);
+    if (p->child) fftb200_plan_destroy(p->child);   // borrows this plan's stream: goes first
     if (p->scratch) cudaFree(p->scratch);
     if (p->fscratch) cudaFree(p->fscratch);
     if (p->fflags) cudaFree(p->fflags);

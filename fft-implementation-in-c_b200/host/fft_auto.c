@@ -56,7 +56,7 @@ fft_plan_t fft_plan_dft_1d(int n, complex_t* in, complex_t* out, int sign, unsig
 
 fft_plan_t fft_plan_r2c_1d(int n, double* in, complex_t* out, unsigned flags) {
     if (n <= 0 || !in || !out) return NULL;
-    if (!is_power_of_two(n)) return NULL;
+    /* any length, like the reference (fft_auto.c:391-403 promotes and plans a c2c, which routes other lengths to Bluestein) */
     return make_plan(n, NULL, in, out, -1, flags | FFT_REAL_INPUT, FFTB200_R2C);
 }
 

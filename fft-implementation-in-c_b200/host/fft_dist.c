@@ -11,6 +11,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <unistd.h>
 
 #define FLAG_BYTES 4096   /* barrier flag area appended to the first exchange buffer */
 
@@ -88,19 +89,26 @@ int fftb200_dist_create(fftb200_dist** out, int log_n, int world, int rank, int 
         d->e2 = fftb200_malloc(bytes);
         if (!d->e0 || !d->e1 || !d->e2) break;
         if (fftb200_memset((char*)d->e0 + bytes, 0, FLAG_BYTES) != 0) break;
-        /* exchange the IPC handles of e0 and e2 */
-        unsigned char mine[128], *all = (unsigned char*)malloc((size_t)128 * (size_t)world);
+        /* exchange the addresses of e0 and e2: CUDA IPC handles for ranks in other processes; ranks that are threads of this
+         * process (one thread per GPU) use the pointers themselves after enabling peer access */
+        struct card { unsigned char h0[64], h2[64]; long long pid; void* p0; void* p2; int device; int pad; } mine, *all;
+        memset(&mine, 0, sizeof(mine));
+        all = (struct card*)malloc(sizeof(struct card) * (size_t)world);
         if (!all) break;
-        int xok = fftb200_ipc_export(d->e0, mine) == 0 && fftb200_ipc_export(d->e2, mine + 64) == 0;
-        if (xok && world > 1) xok = allgather(ctx, mine, all, 128) == 0;
-        else if (xok) memcpy(all, mine, 128);
+        mine.pid = (long long)getpid(); mine.p0 = d->e0; mine.p2 = d->e2; mine.device = fftb200_get_device();
+        int xok = fftb200_ipc_export(d->e0, mine.h0) == 0 && fftb200_ipc_export(d->e2, mine.h2) == 0;
+        if (xok && world > 1) xok = allgather(ctx, &mine, all, sizeof(mine)) == 0;
+        else if (xok) memcpy(all, &mine, sizeof(mine));
         void* b0[64]; void* b2[64]; void* fl[64];
         for (int g = 0; g < world && xok; g++) {
             if (g == rank) { b0[g] = d->e0; b2[g] = d->e2; }
-            else {
-                b0[g] = fftb200_ipc_open(all + 128 * g);
+            else if (all[g].pid == mine.pid) {
+                xok = fftb200_enable_peer_access(all[g].device) == 0;
+                b0[g] = all[g].p0; b2[g] = all[g].p2;
+            } else {
+                b0[g] = fftb200_ipc_open(all[g].h0);
                 if (b0[g]) d->mapped[d->nmapped++] = b0[g];
-                b2[g] = fftb200_ipc_open(all + 128 * g + 64);
+                b2[g] = fftb200_ipc_open(all[g].h2);
                 if (b2[g]) d->mapped[d->nmapped++] = b2[g];
                 xok = b0[g] && b2[g];
             }

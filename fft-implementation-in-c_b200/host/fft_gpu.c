@@ -142,7 +142,7 @@ fftb200_plan* fftb200_host_make_plan(int n, int batch, int direction, int kind) 
     memset(&d, 0, sizeof(d));
     d.n = n; d.batch = batch; d.direction = direction < 0 ? -1 : 1; d.kind = kind;
     double* chirp = NULL;
-    if (kind == FFTB200_BLUESTEIN) {
+    if (kind == FFTB200_BLUESTEIN || (kind == FFTB200_R2C && !is_power_of_two(n))) {   /* real input of any length runs through Bluestein too */
         long long m = 1;
         while (m < 2LL * n - 1) m <<= 1;
         if (m > (1LL << 30)) return NULL;

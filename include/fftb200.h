@@ -130,6 +130,8 @@ int fftb200_stream_sync(void* stream);
 int fftb200_ipc_export(void* dptr, void* handle64);
 void* fftb200_ipc_open(const void* handle64);
 int fftb200_ipc_close(void* mapped);
+/* ranks that are threads of ONE process use each other's pointers directly: enable peer access from the current device */
+int fftb200_enable_peer_access(int peer_device);
 
 /* ---- timing on the plan's stream (CUDA events) ---- */
 int fftb200_timer_start(fftb200_plan* plan);

@@ -15,7 +15,8 @@
  * All data movement between GPUs is done by the kernels over NVLink peer memory (CUDA IPC mappings); the phases are
  * separated by a stream-ordered barrier through peer flags (fftb200_barrier_*). No collective library is linked: the only
  * thing the caller provides is an all-gather of a few hundred bytes at plan time (MPI_Allgather, torch.distributed,
- * a file, ... - see INTEGRATION.md).
+ * a file, ... - see INTEGRATION.md). Ranks may also be threads of one process (one per GPU, programs/demo_dist.c): they are
+ * recognised by their process id and use direct peer access instead of IPC mappings.
  */
 #ifndef FFTB200_DIST_H
 #define FFTB200_DIST_H

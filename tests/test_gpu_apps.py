@@ -227,6 +227,19 @@ def test_demo_drop_in_program(gpu):
     assert "all checks passed" in r.stdout and "FAILED" not in r.stdout
 
 
+def test_distributed_transform_from_plain_c(gpu):
+    """programs/demo_dist.c: fftb200_dist_create / exec_async / sync / destroy from C99, one thread per GPU, the all-gather callback
+    a pthread barrier; every block against the single-GPU plan. Runs with every power-of-two GPU count the box offers."""
+    import subprocess
+    exe = os.path.join(BIN, "demo_dist")
+    assert os.path.exists(exe)
+    g = 1
+    while g <= gpu.lib.fftb200_device_count() and g <= 8:
+        r = subprocess.run([exe, "22" if g == 1 else "24", str(g)], capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0 and "PASS" in r.stdout, r.stdout + r.stderr
+        g *= 2
+
+
 def test_benchmark_program_follows_the_reference_protocol(gpu):
     """benchmarks/benchmark_all.c protocol (sizes, iterations, rand() input, PASS iff reconstruction <= 1e-10)."""
     r = _run(os.path.join(BIN, "benchmark_all_gpu"))

@@ -279,3 +279,53 @@ def test_hermitian_r2c_in_the_fused_kernel(gpu, port, O, n, batch, monkeypatch):
         assert np.array_equal(y1, y2)
     rows = sorted({0, batch - 1})
     assert O.rel_l2(y1[rows], np.stack([port.r2c(x[r]) for r in rows])) <= TOL
+
+
+@pytest.mark.parametrize("n", [1, 3, 12, 360, 1000, 1009, 5000, 100003])
+def test_r2c_of_any_length(gpu, port, O, n):
+    """fft_plan_r2c_1d plans every length like the reference (fft_auto.c:391-403: promote, then a c2c plan, which routes lengths that
+    are not powers of two to Bluestein): promotion, Bluestein c2c and the cut to bins 0 .. n/2 all run on the device."""
+    x = port.fill(82, 0, max(n, 2)).real.copy()[:n]
+    got = gpu.r2c(x)
+    assert got.shape == (n // 2 + 1,)
+    if n <= 8 and n > 2:   # the reference's Bluestein is broken for m <= 16 (missing bit reversal): the true DFT is the yardstick there
+        want = port.naive_dft(x.astype(np.complex128), -1)[: n // 2 + 1]
+    else:
+        want = port.r2c(x)
+    assert O.rel_l2(got, want) <= TOL
+
+
+@pytest.mark.parametrize("log_n", [26, 28, 30])
+def test_single_gpu_plan_against_the_reference_oracle_sketch(gpu, log_n):
+    """One transform of 2^26 / 2^28 / 2^30 points on ONE GPU (three / four tile passes) against the UNMODIFIED reference's split_radix_fft
+    on the same input (seed 45): the host oracle ran once (minutes, 16 GiB at 2^30; tests/golden/make_oracle_2p30.py) and left exact strided
+    bins plus a random-sign sketch of the whole output (tests/sketch.py), so the full vector is checked here without the 16 GiB reference."""
+    import os
+    import sys
+    import torch
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import sketch
+    gold = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    z = np.load(os.path.join(gold, "oracle_2p%d_sketch.npz" % log_n))
+    L = gpu.lib
+    n = 1 << log_n
+    free_b, total_b = torch.cuda.mem_get_info()
+    if free_b < 3.2 * 16 * n + (2 << 30):
+        pytest.skip("needs %d GiB of device memory" % int(3.2 * 16 * n / 2 ** 30 + 2))
+    x = torch.empty(n, dtype=torch.complex128, device="cuda")
+    assert L.fftb200_fill_splitmix(x.data_ptr(), int(z["seed"]), 0, n) == 0
+    plan = L.fft_gpu_plan_1d(n, 1, -1)
+    assert plan, L.fftb200_last_error()
+    assert L.fftb200_plan_exec(L.fftb200_engine_of(plan), x.data_ptr(), x.data_ptr()) == 0, L.fftb200_last_error()
+    L.fft_gpu_destroy_plan(plan)
+    sk, en = sketch.sketch_torch(x, first=0)
+    est = sketch.rel_l2_estimate(sk, z["sketch"], z["energy"])
+    assert est <= TOL, est
+    assert abs(en.sum() - z["energy"].sum()) <= 1e-12 * z["energy"].sum()
+    step = 1 << (log_n - 16)
+    want = np.load(os.path.join(gold, "oracle_2p%d_strided_small.npy" % log_n))
+    got = x[::step].cpu().numpy()
+    assert np.linalg.norm(got - want) / np.linalg.norm(want) <= TOL
+    del x
+    torch.cuda.empty_cache()
+    gpu.lib.fftb200_host_tables_release()   # the 2^30 host table is 16 GiB

@@ -1,0 +1,73 @@
+"""cuFFT yardstick on the same box, side by side with this library (development tool -> profiles/r02_cufft.md).
+The reference's GPU path IS a cuFFT call (gpu/fft_cuda.cu:147-172: cufftPlanMany + cufftExecZ2Z); torch.fft.fft / rfft on complex128 /
+float64 CUDA tensors dispatch to cuFFT Z2Z / D2Z. cuFFT uses accurate twiddles, so it is a SPEED yardstick
+only: it misses the 1e-12 parity bar against the reference for N >= 2^17 like any accurate FFT (the column `cuFFT vs oracle`)."""
+import ctypes as C, json, math, os, sys
+sys.path.insert(0, os.path.join(os.path.dirname(__file__), ".."))
+import numpy as np, torch
+import fftb200_loader
+from oracle import oracle as O
+F = fftb200_loader.load(); L = F.lib
+F.require_gpu()
+p = O.port()
+prop = torch.cuda.get_device_properties(0)
+print("device:", prop.name, "SMs", prop.multi_processor_count, "L2", prop.L2_cache_size >> 20, "MB, memory", prop.total_memory >> 30, "GiB, torch", torch.__version__)
+peak = 6546.9
+try:
+    peak = json.load(open(os.path.join(os.path.dirname(__file__), "..", "MEASURED_PEAKS.json")))["hbm_gbs"]
+except Exception:
+    pass
+
+
+def ev_time(fn, reps=10, warm=3):
+    for _ in range(warm): fn()
+    torch.cuda.synchronize(); ts = []
+    for _ in range(reps):
+        a = torch.cuda.Event(enable_timing=True); b = torch.cuda.Event(enable_timing=True)
+        a.record(); fn(); b.record(); torch.cuda.synchronize(); ts.append(a.elapsed_time(b))
+    return min(ts)
+
+
+def ours(n, batch, kind, din, dout):
+    plan = F.engine_plan(n, batch, kind)
+    ms = C.c_float(); ts = []
+    for i in range(13):
+        L.fftb200_timer_start(plan); assert L.fftb200_plan_exec_async(plan, din, dout) == 0; L.fftb200_timer_stop(plan, C.byref(ms))
+        if i >= 3: ts.append(ms.value)
+    d = L.fftb200_plan_describe(plan).decode().split(": ", 1)[1]
+    L.fftb200_plan_destroy(plan)
+    return min(ts), d
+
+
+print("| config | n | batch | cuFFT ms | this library ms | speed-up | cuFFT strict GB/s (frac of %.0f) | ours strict GB/s (frac) | cuFFT vs oracle (rel L2, last transform) | ours vs oracle | plan |" % peak)
+print("|---|---|---|---|---|---|---|---|---|---|---|")
+cases = [("cfg2", 4096, 65536)] + [("band", 1 << lg, (1 << 28) >> lg) for lg in range(10, 21)] + [("cfg3 single", 1 << 24, 1), ("cfg3 x16", 1 << 24, 16), ("2^22 x64", 1 << 22, 64),
+         ("cfg5 Bluestein", 1000003, 1), ("cfg5 Bluestein x16", 1000003, 16)]
+for tag, n, batch in cases:
+    x = torch.empty(batch, n, dtype=torch.complex128, device="cuda")
+    L.fftb200_fill_splitmix(x.data_ptr(), 43, 0, n * batch)
+    y = torch.empty_like(x)
+    t_cu = ev_time(lambda: torch.fft.fft(x, out=y))
+    want = p.fft(p.fill(43, (batch - 1) * n, n), -1)
+    e_cu = O.rel_l2(y[batch - 1].cpu().numpy(), want)
+    kind = F.FFTB200_C2C if n & (n - 1) == 0 else F.FFTB200_BLUESTEIN
+    t_we, desc = ours(n, batch, kind, x.data_ptr(), y.data_ptr())
+    e_we = O.rel_l2(y[batch - 1].cpu().numpy(), want)
+    b = 32.0 * n * batch
+    print("| %s | %d | %d | %.4f | %.4f | %.2fx | %.0f (%.2f) | %.0f (%.2f) | %.1e | %.1e | %s |" % (tag, n, batch, t_cu, t_we, t_cu / t_we, b / t_cu * 1e-6, b / t_cu * 1e-6 / peak,
+          b / t_we * 1e-6, b / t_we * 1e-6 / peak, e_cu, e_we, desc), flush=True)
+    del x, y
+# real input: cuFFT D2Z against r2c
+for n, batch in ((1 << 20, 256), (1 << 16, 4096), (4096, 65536)):
+    xr = torch.empty(batch, n, dtype=torch.float64, device="cuda")
+    L.fftb200_fill_splitmix(xr.data_ptr(), 47, 0, n * batch // 2)
+    yh = torch.empty(batch, n // 2 + 1, dtype=torch.complex128, device="cuda")
+    t_cu = ev_time(lambda: torch.fft.rfft(xr, out=yh))
+    want = p.r2c(p.fill(47, (batch - 1) * n // 2, n // 2).view(np.float64))
+    e_cu = O.rel_l2(yh[batch - 1].cpu().numpy(), want)
+    t_we, desc = ours(n, batch, F.FFTB200_R2C, xr.data_ptr(), yh.data_ptr())
+    e_we = O.rel_l2(yh[batch - 1].cpu().numpy(), want)
+    b = (8.0 * n + 16.0 * (n // 2 + 1)) * batch
+    print("| r2c (D2Z) | %d | %d | %.4f | %.4f | %.2fx | %.0f (%.2f) | %.0f (%.2f) | %.1e | %.1e | %s |" % (n, batch, t_cu, t_we, t_cu / t_we, b / t_cu * 1e-6, b / t_cu * 1e-6 / peak,
+          b / t_we * 1e-6, b / t_we * 1e-6 / peak, e_cu, e_we, desc), flush=True)
+    del xr, yh
