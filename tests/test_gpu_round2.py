@@ -328,4 +328,6 @@ def test_single_gpu_plan_against_the_reference_oracle_sketch(gpu, log_n):
     assert np.linalg.norm(got - want) / np.linalg.norm(want) <= TOL
     del x
     torch.cuda.empty_cache()
-    gpu.lib.fftb200_host_tables_release()   # the 2^30 host table is 16 GiB
+    L.fftb200_host_tables_release()   # the 2^30 host table is 16 GiB ...
+    L.fft_gpu_cleanup()               # ... and so is the device's cached copy (freed with its last reference)
+    gpu.require_gpu()
