@@ -70,6 +70,7 @@ struct FusedArgs {
     int slots;          // scratch ring depth in groups (>= lag + 1)
     int inverse;        // selects the INV instantiation (conjugate in, conjugate + scale out)
     cd* out;            // r2c mode: output base (the Nyquist bin of every transform is stored by a plain bulk copy)
+    const cd* half_in;  // c2r from the half spectrum: input base (the Nyquist bin of every transform is read by one thread)
     int log_cb;         // column mode: log2 of the 16-column blocks per transform (row length / 16)
     int debug;          // development only: 1 = pass A alone, 2 = pass B alone, 4 = ignore the dependency counters
     double scale;       // 1/N for the inverse
@@ -159,6 +160,11 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* tm, int x, int y
     asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group.L2::cache_hint [%0, {%1, %2}], [%3], %4;"
                  ::"l"(tm), "r"(x), "r"(y), "r"(smem_u32(src)), "l"(pol) : "memory");
 }
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* tm, int c0, int c1, int c2, uint64_t* bar, uint64_t pol) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%2, %3, %4}], [%5], %6;"
+        ::"r"(smem_u32(dst)), "l"(tm), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar)), "l"(pol) : "memory");
+}
 __device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* tm, int c0, int c1, int c2, int c3, uint64_t* bar, uint64_t pol) {
     asm volatile(
         "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%2, %3, %4, %5}], [%6], %7;"
@@ -241,6 +247,28 @@ __device__ __forceinline__ void fused_gather(cd* x, const cd* sm, const G& g) {
         x[bitrev_c<R>(rho)] = y;
     }
 }
+// c2r, first gather of pass A from a tile that holds the half spectrum (see the manager's load): conj(X[c + R t]) for the inverse
+// transform = conj(H) of the direct half, H itself read backwards out of the mirrored half. Column 0 of a transform mirrors onto
+// itself one row down, X[R t] = conj(H[R (M - t)]), and its row M/2 is the Nyquist bin, the one element the tile does not hold.
+template <class G, int R>
+__device__ __forceinline__ void fused_gather_half(cd* x, const cd* sm, const G& g, const bool col0, const cd* nyquist) {
+    const int base = g.gbase();
+#pragma unroll
+    for (int rho = 0; rho < (1 << R); rho++) {
+        const int i = base + rho * G::GSTRIDE;   // logical [t][c] index of the tile; rho >= 2^(R-1) <=> t >= M/2 <=> i >= PIPE_TILE / 2
+        cd y;
+        if (rho < (1 << (R - 1))) {
+            y = sm[i];
+            y.y = -y.y;
+        } else if (!col0) {
+            y = sm[PIPE_TILE + PIPE_TILE / 2 - 1 - i];
+        } else {
+            const int tm = PIPE_TILE - i;          // (M - t) * C for column 0
+            y = tm == PIPE_TILE / 2 ? __ldg(nyquist) : sm[tm];
+        }
+        x[bitrev_c<R>(rho)] = y;
+    }
+}
 template <class G, class SW, int R>
 __device__ __forceinline__ void fused_scatter(const cd* x, cd* sm, const G& g) {
     const int base = g.sbase();
@@ -310,6 +338,8 @@ __device__ __forceinline__ void fused_publish(int* counter) {
 // R2C (forward only): the input is real (n doubles per transform, promoted in the first gather) and only the bins
 // 0 .. n/2 are stored (n/2 + 1 per transform, fft_auto.h:89-97) - the reference's promote-then-c2c reading of
 // fft_plan_r2c_1d without the separate promotion and extraction passes.
+// C2R + HERM: the input is the half spectrum itself (n/2 + 1 bins per transform); the Hermitian extension happens in the tile load (two
+// boxes: the tile's columns and the mirrored columns) and the first gather of pass A - no c2r_expand pass, no full-length work array.
 // C2R (inverse only): the input is the Hermitian-extended spectrum (c2r_expand_kernel), only the real parts of the result are
 // staged and stored (n doubles per transform, fft_auto.h:99-107): the separate real-part pass and its 24 bytes per point go away.
 template <int LM, int LR, bool INV, bool COLS = false, bool R2C = false, bool C2R = false, bool HERM = false>
@@ -320,7 +350,7 @@ fft_fused_kernel(const FusedArgs a, const __grid_constant__ CUtensorMap tm_in, c
     static_assert(!COLS || (LM == 8 && LR == 8), "column mode is built for 256 x 256");
     static_assert(!R2C || (!INV && !COLS), "r2c is a forward transform of whole arrays");
     static_assert(!C2R || (INV && !COLS && !R2C), "c2r is an inverse transform of whole arrays");
-    static_assert(!HERM || R2C, "the Hermitian schedule is a variant of r2c");
+    static_assert(!HERM || R2C || C2R, "the Hermitian variants belong to the real transforms");
     constexpr int LOGN = COLS ? 20 : LM + LR;             // points per (virtual) transform
     constexpr int LOG_TPT = LOGN - 12;
     // HERM: r2c with a Hermitian-aware schedule: the pass-A outputs of a real column satisfy Y_c[M - k] = conj(Y_c[k]), so only the
@@ -331,7 +361,9 @@ fft_fused_kernel(const FusedArgs a, const __grid_constant__ CUtensorMap tm_in, c
     // recurrence (radix2_dit.c:93,109) is not conjugate-symmetric, so its output for real input is Hermitian only to the accuracy of
     // its late-stage twiddles. Measured mismatch against the oracle (profiles/r02_real.md) decides which sizes run this schedule;
     // the others keep the full pass B (R2C without HERM: every column transformed, rows q < R/2 stored).
-    constexpr int TPB = HERM ? (1 << (LOG_TPT - 1)) + 1 : (1 << LOG_TPT);
+    constexpr bool RH = R2C && HERM;   // r2c on the Hermitian schedule
+    constexpr bool CH = C2R && HERM;   // c2r reading the half spectrum
+    constexpr int TPB = RH ? (1 << (LOG_TPT - 1)) + 1 : (1 << LOG_TPT);
     constexpr int LC = 12 - LM, LC2 = 12 - LR;          // log2 columns per A tile / k's per B tile
     constexpr int A3 = LM >= 9, B3 = LR >= 9;            // three sub-passes?
     constexpr int RA0 = A3 ? LM - 8 : LM - 4, RB0 = B3 ? LR - 8 : LR - 4;
@@ -390,7 +422,7 @@ fft_fused_kernel(const FusedArgs a, const __grid_constant__ CUtensorMap tm_in, c
         FusedItem it = cur.locate(sch, first + (long long)w * stride);
         // issue the four quarter loads of tile `x` into the buffer; WAITQ: quarter q only after the store of quarter q has been read
         auto load = [&](const FusedItem& x, auto waitq) {
-            const bool half_b = HERM && x.is_b;   // pass-B tiles of a real transform are numbered 0 .. TPB - 1 per transform
+            const bool half_b = RH && x.is_b;   // pass-B tiles of a real transform are numbered 0 .. TPB - 1 per transform
             const int blk = half_b ? (int)(x.tau % TPB) : (int)(x.tau & ((1 << LOG_TPT) - 1));
             const long long trg = half_b ? x.tau / TPB : x.tau >> LOG_TPT;
             kinds[4 * w] = x.is_b; kinds[4 * w + 1] = blk; kinds[4 * w + 2] = x.g; kinds[4 * w + 3] = (int)trg;
@@ -408,7 +440,13 @@ fft_fused_kernel(const FusedArgs a, const __grid_constant__ CUtensorMap tm_in, c
 #pragma unroll
                 for (int q = 0; q < 4; q++) {
                     waitq(q);
-                    if constexpr (R2C)    // real rows: a quarter is 1024 doubles
+                    if constexpr (CH) {
+                        // the input is the HALF spectrum (N/2 + 1 bins per transform, rows of R): quarters 0, 1 = rows t < M/2 of the tile's columns;
+                        // quarters 2, 3 = the same rows of the mirrored columns R - c0 - C + 1 .. R - c0 - the rows t >= M/2 of the Hermitian
+                        // extension read backwards, X[c + R t] = conj(H[(R - c) + R (M - 1 - t)]) (column R of the first tile is out of range: zeros)
+                        if (q < 2) tma_load_3d(buf + q * QT, &tm_in, 2 * (blk << LC), q * (QT >> LC), (int)tr, &full[w], pol_first);
+                        else tma_load_3d(buf + q * QT, &tm_in, 2 * ((1 << LR) - (blk << LC) - (1 << LC) + 1), (q - 2) * (QT >> LC), (int)tr, &full[w], pol_first);
+                    } else if constexpr (R2C)    // real rows: a quarter is 1024 doubles
                         tma_load_2d(reinterpret_cast<double*>(buf) + q * QT, &tm_in, blk << LC, (int)((tr << LM) + q * (QT >> LC)), &full[w], pol_first);
                     else if constexpr (COLS)   // [b][t_hi][t_lo][c]: 16 columns of block cb, t_lo = blk, a quarter of the t_hi range
                         tma_load_4d(buf + q * QT, &tm_in, 32 * (int)(tr & ((1 << a.log_cb) - 1)), blk, q * 64, (int)(tr >> a.log_cb), &full[w], pol_first);
@@ -459,7 +497,7 @@ fft_fused_kernel(const FusedArgs a, const __grid_constant__ CUtensorMap tm_in, c
             mp[1] += m2 - m1;
 #endif
             {
-                const bool half_b = HERM && cur_it.is_b;
+                const bool half_b = RH && cur_it.is_b;
                 const int blk = half_b ? (int)(cur_it.tau % TPB) : (int)(cur_it.tau & ((1 << LOG_TPT) - 1));
                 const long long trg = half_b ? cur_it.tau / TPB : cur_it.tau >> LOG_TPT;
                 if (!cur_it.is_b) {
@@ -468,7 +506,7 @@ fft_fused_kernel(const FusedArgs a, const __grid_constant__ CUtensorMap tm_in, c
 #pragma unroll
                     for (int q = 0; q < 4; q++) {
                         if constexpr (COLS) tma_store_4d(&tm_sc, 0, blk, q * 64, (int)trl, buf + q * QT, pol_last);   // [slot][k_hi][t_lo][c16]
-                        else if constexpr (HERM) {
+                        else if constexpr (RH) {
                             // rows k < M/2 (two quarters) and the row k = M/2 (C contiguous elements of scratch[c + R k]); the rest is never read
                             if (q < 2) tma_store_2d(&tm_sc, 2 * (blk << LC), (int)((trl << LM) + q * (QT >> LC)), buf + q * QT, pol_last);
                             else if (q == 2)
@@ -484,7 +522,7 @@ fft_fused_kernel(const FusedArgs a, const __grid_constant__ CUtensorMap tm_in, c
                         if constexpr (R2C && !HERM) {   // rows q < R/2 (bins below n/2) are the first two quarters; then the Nyquist bin X[M R/2]
                             if (q < 2) tma_store_3d(&tm_out, 2 * (blk << LC2), q * (QT >> LC2), (int)tr, buf + q * QT, pol_first);
                             else if (q == 2 && blk == 0) bulk_store(a.out + (size_t)tr * ((1 << (LOGN - 1)) + 1) + (1 << (LOGN - 1)), buf + 2 * QT, sizeof(cd));
-                        } else if constexpr (HERM) {
+                        } else if constexpr (RH) {
                             // quarters 0, 1: the bins k + M q, q < R/2, of the tile's columns; quarters 2, 3: the mirrored rows, conj(X[k + M q]) for
                             // q >= R/2 staged as [R - 1 - q][C2 - 1 - (k - k0)] = the bins of the columns M - k0 - C2 + 1 .. M - k0 (column M of the
                             // first tile - the mirror of k = 0, which that tile produces directly - falls off the tensor and is dropped).
@@ -576,6 +614,20 @@ fft_fused_kernel(const FusedArgs a, const __grid_constant__ CUtensorMap tm_in, c
                     // the complex results overwrite other threads' real inputs: gather everything first
 #pragma unroll
                     for (int bb = 0; bb < NB; bb++) fused_gather_real<G0, RA0>(&x[bb * R0], sm, G0(t + PIPE_GROUP * bb));
+                    group_sync(g2);
+#pragma unroll
+                    for (int bb = 0; bb < NB; bb++) {
+                        SubStageExact<RA0, 1, 0, 0>::run(&x[bb * R0]);
+                        fused_scatter<G0, SwzId, RA0>(&x[bb * R0], sm, G0(t + PIPE_GROUP * bb));
+                    }
+                } else if constexpr (CH) {
+                    // the complex results overwrite other threads' half-spectrum inputs (the mirrored half is read backwards): gather everything first
+                    const cd* nyq = a.half_in + ((size_t)kg * a.gt + ktr) * (((size_t)1 << (LOGN - 1)) + 1) + ((size_t)1 << (LOGN - 1));
+#pragma unroll
+                    for (int bb = 0; bb < NB; bb++) {
+                        const G0 g(t + PIPE_GROUP * bb);
+                        fused_gather_half<G0, RA0>(&x[bb * R0], sm, g, kb == 0 && g.lo == 0, nyq);
+                    }
                     group_sync(g2);
 #pragma unroll
                     for (int bb = 0; bb < NB; bb++) {
@@ -725,7 +777,7 @@ fft_fused_kernel(const FusedArgs a, const __grid_constant__ CUtensorMap tm_in, c
                     double* p = reinterpret_cast<double*>(sm) + gl.hi + (gl.kloc << LC2);
 #pragma unroll
                     for (int q = 0; q < 16; q++) p[q << (AL + LC2)] = x[q].x * sc;
-                } else if constexpr (HERM) {
+                } else if constexpr (RH) {
                     // q' < 8 (q < R/2): [q][k] as ever; q' >= 8: the conjugate at [R - 1 - q][C2 - 1 - k] of the second half of the buffer
                     cd* p = sm + gl.hi + (gl.kloc << LC2);
                     cd* pm = sm + PIPE_TILE / 2 + (((1 << LR) - 1 - gl.kloc) << LC2) + ((1 << LC2) - 1 - gl.hi);
@@ -778,15 +830,15 @@ const void* fused_r2c_func_0(int lm, int lr, int herm);
 const void* fused_r2c_func_1(int lm, int lr, int herm);
 const void* fused_r2c_func_2(int lm, int lr, int herm);
 const void* fused_r2c_func_3(int lm, int lr, int herm);
-const void* fused_c2r_func_0(int lm, int lr);
-const void* fused_c2r_func_1(int lm, int lr);
-const void* fused_c2r_func_2(int lm, int lr);
-const void* fused_c2r_func_3(int lm, int lr);
-inline const void* fused_c2r_func(int lm, int lr) {
-    const void* f = fused_c2r_func_0(lm, lr);
-    if (!f) f = fused_c2r_func_1(lm, lr);
-    if (!f) f = fused_c2r_func_2(lm, lr);
-    if (!f) f = fused_c2r_func_3(lm, lr);
+const void* fused_c2r_func_0(int lm, int lr, int herm);
+const void* fused_c2r_func_1(int lm, int lr, int herm);
+const void* fused_c2r_func_2(int lm, int lr, int herm);
+const void* fused_c2r_func_3(int lm, int lr, int herm);
+inline const void* fused_c2r_func(int lm, int lr, int herm) {
+    const void* f = fused_c2r_func_0(lm, lr, herm);
+    if (!f) f = fused_c2r_func_1(lm, lr, herm);
+    if (!f) f = fused_c2r_func_2(lm, lr, herm);
+    if (!f) f = fused_c2r_func_3(lm, lr, herm);
     return f;
 }
 inline const void* fused_r2c_func(int lm, int lr, int herm) {

@@ -295,6 +295,7 @@ struct fftb200_plan {
     cd* work = nullptr;        // Bluestein / R2C: padded complex work array, m * batch
     fftb200_plan* child = nullptr;   // R2C of a non-power-of-two length: the Bluestein c2c plan that transforms the promoted input
     bool r2c_herm = false;     // R2C of 2^14 .. : the fused kernel transforms only the columns k <= M/2 in pass B (fft_fused.cuh, HERM)
+    bool c2r_half = false;     // fused C2R that reads the half spectrum itself (no c2r_expand pass, no work array)
     bool fused_c2r = false;    // C2R of 2^14 .. 2^20 points: the fused kernel stores the real parts itself
     bool pipe_blue = false;    // Bluestein with m = 512 .. 4096: both transforms in the pipe kernel's Bluestein variants, no elementwise kernels
     bool pipe_real = false;    // R2C / C2R of 512 .. 4096 points: the pipe kernel reads reals / half spectra itself (no work array)
@@ -582,8 +583,20 @@ static int enqueue_fused(fftb200_plan* p, const Pass& ps, const cd* in, cd* out,
                 CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled failed (%d) for the cut-off half spectrum", (int)r);
     }
+    const bool c2r_half = r2c == 2 && p->c2r_half;
+    if (c2r_half) {
+        // half spectra, N/2 + 1 bins per transform: rows t < M/2 of R bins each, a quarter of a pass-A tile is the box C x M/4 (fft_fused.cuh, C2R + HERM)
+        const cuuint64_t hdim[3] = {(cuuint64_t)2 << lr, (cuuint64_t)1 << (lm - 1), (cuuint64_t)nbatch};
+        const cuuint64_t hstr[2] = {(cuuint64_t)sizeof(cd) << lr, (cuuint64_t)sizeof(cd) * (((cuuint64_t)1 << (L - 1)) + 1)};
+        const cuuint32_t hbox[3] = {(cuuint32_t)2 << (12 - lm), (cuuint32_t)1 << (lm - 2), 1};
+        const cuuint32_t estr[3] = {1, 1, 1};
+        const CUresult r = enc(&tm[0], CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, (void*)in, hdim, hstr, hbox, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                               CU_TENSOR_MAP_SWIZZLE_NONE, pr, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled failed (%d) for the half-spectrum input", (int)r);
+    }
     for (int i = 0; i < 3 && !cols; i++) {
         if (r2c == 1 && i != 1) continue;
+        if (c2r_half && i == 0) continue;
         const int lcols = i == 2 ? lm : lr, lrows = i == 2 ? lr : lm;          // row length / rows per transform (log2)
         const long long ntr = i == 1 ? slots * gt : nbatch;
         void* base = i == 0 ? (void*)in : i == 1 ? (void*)p->fscratch : (void*)out;
@@ -621,7 +634,7 @@ static int enqueue_fused(fftb200_plan* p, const Pass& ps, const cd* in, cd* out,
     FusedArgs fa;
     fa.scratch = p->fscratch; fa.tab = p->tab; fa.acc = p->acc; fa.flags = p->fflags;
     fa.nbatch = nbatch; fa.gt = (int)gt; fa.ngroups = (int)G; fa.lag = (int)lag; fa.slots = (int)slots;
-    fa.inverse = inverse; fa.scale = cols ? 1.0 : p->scale; fa.log_cb = log_cb; fa.out = out;
+    fa.inverse = inverse; fa.scale = cols ? 1.0 : p->scale; fa.log_cb = log_cb; fa.out = out; fa.half_in = in;
     fa.debug = getenv("FFTB200_FUSED_DEBUG") ? atoi(getenv("FFTB200_FUSED_DEBUG")) : 0;
     memcpy(fa.dtw, p->fdtw, sizeof(fa.dtw));
     fa.prof = nullptr;
@@ -634,7 +647,7 @@ static int enqueue_fused(fftb200_plan* p, const Pass& ps, const cd* in, cd* out,
     const bool herm = r2c == 1 && p->r2c_herm;
     const long long items = herm ? nbatch * (tpt + tpt / 2 + 1) : 2 * nbatch * tpt;   // Hermitian schedule: pass B on the columns k <= M/2 only
     const int grid = (int)(items < ps.grid_max ? items : ps.grid_max);
-    const void* func = r2c == 1 ? fused_r2c_func(lm, lr, herm) : r2c == 2 ? fused_c2r_func(lm, lr) : cols ? fused_cols_func(inverse) : fused_func(lm, lr, inverse);
+    const void* func = r2c == 1 ? fused_r2c_func(lm, lr, herm) : r2c == 2 ? fused_c2r_func(lm, lr, c2r_half) : cols ? fused_cols_func(inverse) : fused_func(lm, lr, inverse);
     if (!func) return fail("no fused kernel for 2^%d x 2^%d", lm, lr);
     CU(launch_fused(func, fa, tm, grid, p->stream));
 #ifdef FUSED_PROF
@@ -898,15 +911,21 @@ extern "C" int fftb200_plan_create(fftb200_plan** out, const fftb200_plan_desc* 
         } else
         if (d->kind == FFTB200_C2R) {
             // Hermitian extension -> inverse c2c of the full length with the reference's stage operators -> real parts
-            p->work = (cd*)fftb200_malloc(sizeof(cd) * (size_t)p->m * (size_t)p->batch);
-            if (!p->work) { rc = -1; break; }
             p->fused_c2r = p->passes.size() == 1 && p->passes[0].fused_lm && !getenv("FFTB200_NO_FUSED_C2R") &&
-                           fused_c2r_func(p->passes[0].fused_lm, p->passes[0].fused_lr);
+                           fused_c2r_func(p->passes[0].fused_lm, p->passes[0].fused_lr, 0);
+            // 2^14 .. 2^20: the fused kernel reads the half spectrum itself - the extension happens in its tile loads and first gather
+            // (same values, same arithmetic: bit-identical to the separate c2r_expand pass, which FFTB200_C2R_HERMITIAN=0 keeps)
+            p->c2r_half = p->fused_c2r && !(getenv("FFTB200_C2R_HERMITIAN") && atoi(getenv("FFTB200_C2R_HERMITIAN")) == 0);
+            if (!p->c2r_half) {
+                p->work = (cd*)fftb200_malloc(sizeof(cd) * (size_t)p->m * (size_t)p->batch);
+                if (!p->work) { rc = -1; break; }
+            }
             if (p->fused_c2r) {
-                if (cudaFuncSetAttribute(fused_c2r_func(p->passes[0].fused_lm, p->passes[0].fused_lr), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                if (cudaFuncSetAttribute(fused_c2r_func(p->passes[0].fused_lm, p->passes[0].fused_lr, p->c2r_half), cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)FUSED_SMEM) != cudaSuccess) { rc = fail("cudaFuncSetAttribute failed"); break; }
-                p->launches += 1;
-                p->desc += " [hermitian extension + inverse c2c storing the real parts]";
+                p->launches += p->c2r_half ? 0 : 1;
+                p->desc += p->c2r_half ? " [half spectrum in (extension in the tile loads), inverse c2c storing the real parts]"
+                                       : " [hermitian extension + inverse c2c storing the real parts]";
             } else {
                 p->launches += 2;
                 p->desc += " [hermitian extension + inverse c2c + real parts]";
@@ -1206,7 +1225,7 @@ static int exec_range(fftb200_plan* p, const void* d_in, void* d_out, long long 
         CU(cudaGetLastError());
         return 0;
     }
-    if ((p->kind == FFTB200_R2C || p->kind == FFTB200_C2R) && (p->pipe_real || (p->kind == FFTB200_R2C && !p->work)) && nbatch > 0) {
+    if ((p->kind == FFTB200_R2C || p->kind == FFTB200_C2R) && (p->pipe_real || !p->work) && nbatch > 0) {
         // the single-kernel real transforms read packed rows that other CTAs' outputs would overwrite: out of place only
         const size_t half = sizeof(cd) * (n / 2 + 1), full = sizeof(double) * n;
         const char* i0 = (const char*)d_in; const char* o0 = (const char*)d_out;
@@ -1227,6 +1246,11 @@ static int exec_range(fftb200_plan* p, const void* d_in, void* d_out, long long 
     if (p->kind == FFTB200_C2R) {
         if (nbatch <= 0) return 0;
         const size_t nh = n / 2 + 1;
+        if (p->c2r_half) {
+            if (enqueue_fused(p, p->passes[0], (const cd*)d_in, (cd*)d_out, 1, nbatch, 2) != 0) return -1;
+            CU(cudaGetLastError());
+            return 0;
+        }
         c2r_expand_kernel<<<grid_for(total), 256, 0, p->stream>>>(p->work, (const cd*)d_in, n, nh, total);
         if (p->fused_c2r) {
             if (enqueue_fused(p, p->passes[0], p->work, (cd*)d_out, 1, nbatch, 2) != 0) return -1;

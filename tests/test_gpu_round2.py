@@ -160,30 +160,31 @@ def test_multi_device_fan_out_behind_the_batch_entry_point(gpu, port, O, n, batc
     assert O.rel_l2(one[rows], want) <= TOL
 
 
-@pytest.mark.parametrize("n", [512, 4096, 1 << 14])
+@pytest.mark.parametrize("n", [512, 4096, 1 << 14, 1 << 17])
 def test_single_kernel_real_transforms_reject_overlapping_buffers(gpu, port, n):
     """r2c / c2r plans whose kernel reads packed rows (pipe variants 512 .. 4096, fused r2c) run out of place: an aliased call fails
     with an error instead of racing."""
     import torch
     L = gpu.lib
     batch = 40
-    buf = torch.zeros(batch * (n + 2), dtype=torch.complex128, device="cuda")
+    buf = torch.zeros(batch * (n + 2), dtype=torch.complex128, device="cuda")   # room for either side of either transform
+    other = torch.zeros(batch * (n + 2), dtype=torch.complex128, device="cuda")
     p = gpu.engine_plan(n, batch, gpu.FFTB200_R2C)
     assert L.fftb200_plan_exec(p, buf.data_ptr(), buf.data_ptr()) != 0
     assert b"out of place" in L.fftb200_last_error()
-    assert L.fftb200_plan_exec(p, buf.data_ptr(), buf.data_ptr() + 16 * batch * n) == 0
+    assert L.fftb200_plan_exec(p, buf.data_ptr(), buf.data_ptr() + 8 * batch * n - 16) != 0   # the last input double overlaps the first bin
+    assert L.fftb200_plan_exec(p, buf.data_ptr(), other.data_ptr()) == 0
     L.fftb200_plan_destroy(p)
-    if n <= 4096:
-        p = gpu.engine_plan(n, batch, gpu.FFTB200_C2R, 1)
-        assert L.fftb200_plan_exec(p, buf.data_ptr(), buf.data_ptr()) != 0
-        L.fftb200_plan_destroy(p)
+    p = gpu.engine_plan(n, batch, gpu.FFTB200_C2R, 1)   # pipe variants up to 4096, the fused kernel reading half spectra above
+    assert L.fftb200_plan_exec(p, buf.data_ptr(), buf.data_ptr()) != 0
+    L.fftb200_plan_destroy(p)
 
 
 def test_c2r_in_place_where_it_is_allowed(gpu, port, O):
-    """c2r outside the single-kernel sizes goes through the plan's work array: in place is fine."""
+    """c2r outside the single-kernel sizes (here 2^21: three tile passes) goes through the plan's work array: in place is fine."""
     import torch
     L = gpu.lib
-    n, batch = 1 << 15, 9
+    n, batch = 1 << 21, 3
     x = port.fill(66, 0, n * batch).real.copy().reshape(batch, n)
     half = np.fft.rfft(x, axis=1)
     p = gpu.engine_plan(n, batch, gpu.FFTB200_C2R, 1)
@@ -191,8 +192,42 @@ def test_c2r_in_place_where_it_is_allowed(gpu, port, O):
     buf[:half.size] = torch.from_numpy(half.ravel()).cuda()
     assert L.fftb200_plan_exec(p, buf.data_ptr(), buf.data_ptr()) == 0
     got = torch.view_as_real(buf).ravel()[:batch * n].cpu().numpy().reshape(batch, n)
-    assert O.rel_l2(got, x) <= 1e-11
+    assert O.rel_l2(got, x) <= 1e-10   # against numpy's accurate inverse: the reference's own arithmetic is 2e-11 from it here
     L.fftb200_plan_destroy(p)
+
+
+@pytest.mark.parametrize("n,batch", [(1 << 14, 1), (1 << 14, 77), (1 << 15, 40), (1 << 16, 9), (1 << 17, 5), (1 << 18, 3), (1 << 19, 2), (1 << 20, 3)])
+def test_c2r_reads_the_half_spectrum_inside_the_fused_kernel(gpu, port, O, n, batch, monkeypatch):
+    """c2r of 2^14 .. 2^20 points: the fused inverse kernel loads the half spectrum itself - each pass-A tile is two boxes, its own columns and
+    the mirrored ones, and the first gather reads the mirrored half backwards (fft_fused.cuh, C2R + HERM). FFTB200_C2R_HERMITIAN=0 keeps the
+    separate c2r_expand pass over a full-length work array: the same values through the same arithmetic, so the outputs are identical bit for
+    bit (unlike r2c, nothing is approximated here: the extension X[N - j] = conj X[j] IS the definition of c2r). Rows against the oracle."""
+    import torch
+    L = gpu.lib
+    x = port.fill(83, 0, n * batch).real.copy().reshape(batch, n)
+    half = np.fft.rfft(x, axis=1)
+    half[:, 0] += 0.25j * np.arange(1, batch + 1)     # imaginary parts in bin 0 / Nyquist: both paths must treat them alike
+    half[:, -1] -= 0.5j
+    hd = torch.from_numpy(half).cuda()
+
+    def run():
+        plan = gpu.engine_plan(n, batch, gpu.FFTB200_C2R, direction=1)
+        desc = L.fftb200_plan_describe(plan).decode()
+        yd = torch.full((batch, n), float("nan"), dtype=torch.float64, device="cuda")
+        for _ in range(2):
+            assert L.fftb200_plan_exec(plan, hd.data_ptr(), yd.data_ptr()) == 0, L.fftb200_last_error()
+        L.fftb200_plan_destroy(plan)
+        return yd.cpu().numpy(), desc
+    y1, d1 = run()
+    assert "half spectrum in" in d1, d1
+    monkeypatch.setenv("FFTB200_C2R_HERMITIAN", "0")
+    y2, d2 = run()
+    monkeypatch.delenv("FFTB200_C2R_HERMITIAN")
+    assert "hermitian extension" in d2, d2
+    assert np.isfinite(y1).all()
+    assert np.array_equal(y1, y2)
+    rows = sorted({0, batch - 1})
+    assert O.rel_l2(y1[rows], np.stack([port.c2r(half[r], n) for r in rows])) <= TOL
 
 
 def test_cleanup_keeps_the_tables_of_live_plans(gpu, port, O):
