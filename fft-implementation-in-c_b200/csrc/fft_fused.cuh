@@ -54,6 +54,9 @@
 #ifndef FUSED_BDIRECT
 #define FUSED_BDIRECT 1
 #endif
+#ifndef FUSED_R2C_MIRROR
+#define FUSED_R2C_MIRROR 1
+#endif
 
 namespace fftb200 {
 
@@ -247,6 +250,17 @@ __device__ __forceinline__ void fused_gather(cd* x, const cd* sm, const G& g) {
         x[bitrev_c<R>(rho)] = y;
     }
 }
+// r2c, first gather of a pass-B tile that may hold the rows M - k of its columns (flip = the row field complemented): Y[M - k] = conj Y[k]
+template <class G, int R>
+__device__ __forceinline__ void fused_gather_mirror(cd* x, const cd* sm, const G& g, const int flip, const bool conj) {
+    const int base = g.gbase() ^ flip;
+#pragma unroll
+    for (int rho = 0; rho < (1 << R); rho++) {
+        cd y = sm[base + rho * G::GSTRIDE];
+        if (conj) y.y = -y.y;
+        x[bitrev_c<R>(rho)] = y;
+    }
+}
 // c2r, first gather of pass A from a tile that holds the half spectrum (see the manager's load): conj(X[c + R t]) for the inverse
 // transform = conj(H) of the direct half, H itself read backwards out of the mirrored half. Column 0 of a transform mirrors onto
 // itself one row down, X[R t] = conj(H[R (M - t)]), and its row M/2 is the Nyquist bin, the one element the tile does not hold.
@@ -363,6 +377,11 @@ fft_fused_kernel(const FusedArgs a, const __grid_constant__ CUtensorMap tm_in, c
     // the others keep the full pass B (R2C without HERM: every column transformed, rows q < R/2 stored).
     constexpr bool RH = R2C && HERM;   // r2c on the Hermitian schedule
     constexpr bool CH = C2R && HERM;   // c2r reading the half spectrum
+    // RM: r2c with the full pass B (every size above R2C_HERM_MAX_LOG). Pass A still stores only the rows k <= M/2: its outputs ARE
+    // Hermitian in k to rounding (stages m <= 1024, conjugate-symmetric tables), so a pass-B tile of columns k > M/2 loads the block of
+    // rows M - k instead and reads it backwards and conjugated in its first gather. Pass B itself - the late stages with the reference's
+    // twiddles, where the symmetry does not hold to 1e-12 - runs on every column as before: half of the pass-A scratch stores for free.
+    constexpr bool RM = R2C && !HERM && FUSED_R2C_MIRROR;
     constexpr int TPB = RH ? (1 << (LOG_TPT - 1)) + 1 : (1 << LOG_TPT);
     constexpr int LC = 12 - LM, LC2 = 12 - LR;          // log2 columns per A tile / k's per B tile
     constexpr int A3 = LM >= 9, B3 = LR >= 9;            // three sub-passes?
@@ -429,7 +448,9 @@ fft_fused_kernel(const FusedArgs a, const __grid_constant__ CUtensorMap tm_in, c
             mbar_expect_tx(&full[w], (R2C && !x.is_b) ? PIPE_TILE * (uint32_t)sizeof(double) : PIPE_TILE * (uint32_t)sizeof(cd));
             if (x.is_b) {
                 asm volatile("fence.proxy.async;" ::: "memory");
-                const cd* src = a.scratch + ((((size_t)(x.g % a.slots) * a.gt) + (size_t)trg) << LOGN) + (size_t)blk * PIPE_TILE;
+                // (RM: a tile of columns k0 .. k0 + C2 - 1 above M/2 loads the rows M - k0 - C2 + 1 .. M - k0 instead: the same bytes count, read backwards)
+                const size_t row0 = (RM && blk >= (1 << (LOG_TPT - 1))) ? ((size_t)1 << LM) - ((size_t)blk << LC2) - ((size_t)1 << LC2) + 1 : (size_t)blk << LC2;
+                const cd* src = a.scratch + ((((size_t)(x.g % a.slots) * a.gt) + (size_t)trg) << LOGN) + (row0 << LR);
 #pragma unroll
                 for (int q = 0; q < 4; q++) {
                     waitq(q);
@@ -506,7 +527,7 @@ fft_fused_kernel(const FusedArgs a, const __grid_constant__ CUtensorMap tm_in, c
 #pragma unroll
                     for (int q = 0; q < 4; q++) {
                         if constexpr (COLS) tma_store_4d(&tm_sc, 0, blk, q * 64, (int)trl, buf + q * QT, pol_last);   // [slot][k_hi][t_lo][c16]
-                        else if constexpr (RH) {
+                        else if constexpr (RH || RM) {
                             // rows k < M/2 (two quarters) and the row k = M/2 (C contiguous elements of scratch[c + R k]); the rest is never read
                             if (q < 2) tma_store_2d(&tm_sc, 2 * (blk << LC), (int)((trl << LM) + q * (QT >> LC)), buf + q * QT, pol_last);
                             else if (q == 2)
@@ -722,10 +743,20 @@ fft_fused_kernel(const FusedArgs a, const __grid_constant__ CUtensorMap tm_in, c
             {
                 typedef Geo<0, LR, LC2, 0, RB0, false> G0;
                 constexpr int NB = 16 >> RB0, R0 = 1 << RB0;
+                if constexpr (RM) {
+                    // 0: the tile's own rows; 1: the rows M - k, backwards and conjugated; 2: the tile that starts at k = M/2 (its first row is its own)
+                    const int mode = kb < (1 << (LOG_TPT - 1)) ? 0 : kb == (1 << (LOG_TPT - 1)) ? 2 : 1;
 #pragma unroll
-                for (int bb = 0; bb < NB; bb++) {
-                    const G0 g(t + PIPE_GROUP * bb);
-                    fused_gather<G0, SwzId, RB0, false>(&x[bb * R0], sm, g);
+                    for (int bb = 0; bb < NB; bb++) {
+                        const G0 g(t + PIPE_GROUP * bb);
+                        fused_gather_mirror<G0, RB0>(&x[bb * R0], sm, g, mode ? ((1 << LC2) - 1) << LR : 0, mode == 1 || (mode == 2 && g.hi != 0));
+                    }
+                } else {
+#pragma unroll
+                    for (int bb = 0; bb < NB; bb++) {
+                        const G0 g(t + PIPE_GROUP * bb);
+                        fused_gather<G0, SwzId, RB0, false>(&x[bb * R0], sm, g);
+                    }
                 }
                 cd tw[R0];
 #pragma unroll

@@ -5,6 +5,7 @@ out-of-place rule of the single-kernel real transforms, cleanup with live plans.
 Bar as everywhere: relative L2 <= 1e-12 against the reference's CPU arithmetic (oracle/fft_oracle.c, pinned to the compiled
 reference by tests/test_oracle.py)."""
 import ctypes as C
+import os
 import threading
 import time
 
@@ -305,13 +306,15 @@ def test_hermitian_r2c_in_the_fused_kernel(gpu, port, O, n, batch, monkeypatch):
         direct = k <= (1 << lm) // 2
         assert np.array_equal(y1[:, direct], y2[:, direct])
         assert O.rel_l2(y1, y2) <= 5e-13
-        # forcing the schedule off gives the full pass B: identical to the promoted path everywhere
+        # forcing the schedule off gives the full pass B on every column: the promoted path's result to the last bits
         monkeypatch.setenv("FFTB200_R2C_HERMITIAN", "0")
         y3, d3 = run()
         monkeypatch.delenv("FFTB200_R2C_HERMITIAN")
-        assert "columns k <= M/2" not in d3 and np.array_equal(y3, y2)
+        assert "columns k <= M/2" not in d3 and O.rel_l2(y3, y2) <= 2e-15
     elif n > (1 << 16):
-        assert np.array_equal(y1, y2)
+        # full pass B on every column; the pass-A rows above M/2 are read as conjugates of the rows M - k (Hermitian to rounding: stages m <= 1024
+        # with conjugate-symmetric tables), so the two paths agree to the last bits, not bit for bit
+        assert O.rel_l2(y1, y2) <= 2e-15
     rows = sorted({0, batch - 1})
     assert O.rel_l2(y1[rows], np.stack([port.r2c(x[r]) for r in rows])) <= TOL
 
@@ -366,3 +369,17 @@ def test_single_gpu_plan_against_the_reference_oracle_sketch(gpu, log_n):
     L.fftb200_host_tables_release()   # the 2^30 host table is 16 GiB ...
     L.fft_gpu_cleanup()               # ... and so is the device's cached copy (freed with its last reference)
     gpu.require_gpu()
+
+
+def test_random_shapes_against_numpy(gpu):
+    """A bounded run of tools/fuzz.py (every kind of plan at random n / batch / direction / in-place against numpy's accurate transform):
+    catches gross errors - a wrong tile, a race, a ragged batch - that fixed-size parity tests can miss. 25 s, fixed seed."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "tools", "fuzz.py"), "25", "7"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    last = [l for l in r.stdout.splitlines() if l.startswith("{")][-1]
+    res = json.loads(last)
+    assert res.get("bad", []) == [] and res.get("runs", 0) >= 20, last
