@@ -57,6 +57,9 @@
 #ifndef FUSED_R2C_MIRROR
 #define FUSED_R2C_MIRROR 1
 #endif
+#ifndef FUSED_R2C_PACK
+#define FUSED_R2C_PACK 1
+#endif
 
 namespace fftb200 {
 
@@ -82,7 +85,8 @@ struct FusedArgs {
 
 constexpr int FUSED_THREADS = 2 * PIPE_GROUP + 32 * PIPE_STAGES;   // two compute groups + one manager warp per ring buffer
 constexpr int FUSED_TW1 = 16 * 8, FUSED_TW2 = 64 * 8;
-constexpr size_t FUSED_SMEM = (size_t)PIPE_STAGES * PIPE_TILE * sizeof(cd) + (FUSED_TW1 + FUSED_TW2) * sizeof(cd) + 256;
+constexpr int FUSED_ROWH = 64;   // r2c: the pass-A row k = M/2 of a tile (2C <= 64 complex), staged beside each ring buffer
+constexpr size_t FUSED_SMEM = (size_t)PIPE_STAGES * PIPE_TILE * sizeof(cd) + (FUSED_TW1 + FUSED_TW2 + PIPE_STAGES * FUSED_ROWH) * sizeof(cd) + 256;
 
 // ---- tile geometry: logical index I = lo + 2^LB * f + 2^(LB+LP) * hi, f = LP-bit transform field -------------
 // Sub-pass (A stages done, radix 2^R): butterfly (lo, c'', kloc, hi) gathers f = c'' + 2^(LP-A-R) rho + 2^(LP-A) kloc
@@ -198,12 +202,13 @@ __device__ __forceinline__ void bulk_load_hint(void* dst, const void* src, uint3
 struct FusedSched {
     long long nbatch;
     int gt, G, L, log_tpt, a_on, b_on;
+    int log_tpa;   // pass-A tiles per transform (log2): log_tpt, or one less when a tile holds twice the columns (packed real input)
     int tpb;   // pass-B tiles per transform: 2^log_tpt, or 2^(log_tpt - 1) + 1 when only the columns k <= M/2 are transformed (real input)
     __device__ __forceinline__ long long transforms_of(int g) const {
         long long nb = nbatch - (long long)g * gt;
         return nb > gt ? gt : nb;
     }
-    __device__ __forceinline__ long long tiles_of(int g) const { return transforms_of(g) << log_tpt; }   // pass A
+    __device__ __forceinline__ long long tiles_of(int g) const { return transforms_of(g) << log_tpa; }   // pass A
     __device__ __forceinline__ long long tiles_b(int g) const { return transforms_of(g) * tpb; }        // pass B
     __device__ __forceinline__ long long round_len(int rho) const {
         long long n = 0;
@@ -382,6 +387,12 @@ fft_fused_kernel(const FusedArgs a, const __grid_constant__ CUtensorMap tm_in, c
     // rows M - k instead and reads it backwards and conjugated in its first gather. Pass B itself - the late stages with the reference's
     // twiddles, where the symmetry does not hold to 1e-12 - runs on every column as before: half of the pass-A scratch stores for free.
     constexpr bool RM = R2C && !HERM && FUSED_R2C_MIRROR;
+    // PACK: a pass-A tile of a real transform holds 2C real columns = C complex columns z = x[2c'] + i x[2c' + 1] as they lie in memory
+    // (a row of 2C doubles IS a row of C complex numbers): one complex M-point transform per pair, then the unpack step
+    // Y[2c'][k] = (Z[k] + conj Z[M - k]) / 2, Y[2c' + 1][k] = (Z[k] - conj Z[M - k]) / 2i for k <= M/2 - half of the pass-A tiles and
+    // arithmetic. Pass A uses the accurate tables, so this regrouping is exact to rounding like every other use of them (hybrid rule).
+    constexpr bool PACK = R2C && FUSED_R2C_PACK && (RH || RM);
+    constexpr int LOG_TPA = PACK ? LOG_TPT - 1 : LOG_TPT;
     constexpr int TPB = RH ? (1 << (LOG_TPT - 1)) + 1 : (1 << LOG_TPT);
     constexpr int LC = 12 - LM, LC2 = 12 - LR;          // log2 columns per A tile / k's per B tile
     constexpr int A3 = LM >= 9, B3 = LR >= 9;            // three sub-passes?
@@ -398,15 +409,16 @@ fft_fused_kernel(const FusedArgs a, const __grid_constant__ CUtensorMap tm_in, c
     cd* const bufs = reinterpret_cast<cd*>(smem_raw);
     cd* const tw1s = bufs + (size_t)PIPE_STAGES * PIPE_TILE;
     cd* const tw2s = tw1s + FUSED_TW1;
-    uint64_t* const full = reinterpret_cast<uint64_t*>(tw2s + FUSED_TW2);   // [3] tile loaded
+    uint64_t* const full = reinterpret_cast<uint64_t*>(smem_raw + FUSED_SMEM - 256);   // [3] tile loaded (the last 256 bytes: barriers + kinds)
     uint64_t* const staged = full + PIPE_STAGES;                            // [3] result staged in place by a compute group
     volatile int* const kinds = reinterpret_cast<volatile int*>(staged + PIPE_STAGES);   // [3][4]: is_b, kb, g of the loaded tile
+    cd* const rowh = reinterpret_cast<cd*>(smem_raw + FUSED_SMEM - 256) - PIPE_STAGES * FUSED_ROWH;   // [3][64] (r2c, PACK)
 
     FusedSched sch;
-    sch.nbatch = a.nbatch; sch.gt = a.gt; sch.G = a.ngroups; sch.L = a.lag; sch.log_tpt = LOG_TPT; sch.tpb = TPB;
+    sch.nbatch = a.nbatch; sch.gt = a.gt; sch.G = a.ngroups; sch.L = a.lag; sch.log_tpt = LOG_TPT; sch.log_tpa = LOG_TPA; sch.tpb = TPB;
     sch.a_on = !(a.debug & 2); sch.b_on = !(a.debug & 1);
     const bool nowait = (a.debug & 7) != 0;
-    const long long total = a.nbatch * (((long long)sch.a_on << LOG_TPT) + (long long)sch.b_on * TPB);
+    const long long total = a.nbatch * (((long long)sch.a_on << LOG_TPA) + (long long)sch.b_on * TPB);
     const int first = blockIdx.x, stride = gridDim.x;
     const int my_tiles = first < total ? (int)((total - first + stride - 1) / stride) : 0;
 
@@ -442,10 +454,11 @@ fft_fused_kernel(const FusedArgs a, const __grid_constant__ CUtensorMap tm_in, c
         // issue the four quarter loads of tile `x` into the buffer; WAITQ: quarter q only after the store of quarter q has been read
         auto load = [&](const FusedItem& x, auto waitq) {
             const bool half_b = RH && x.is_b;   // pass-B tiles of a real transform are numbered 0 .. TPB - 1 per transform
-            const int blk = half_b ? (int)(x.tau % TPB) : (int)(x.tau & ((1 << LOG_TPT) - 1));
-            const long long trg = half_b ? x.tau / TPB : x.tau >> LOG_TPT;
+            const int ltp = x.is_b ? LOG_TPT : LOG_TPA;
+            const int blk = half_b ? (int)(x.tau % TPB) : (int)(x.tau & ((1 << ltp) - 1));
+            const long long trg = half_b ? x.tau / TPB : x.tau >> ltp;
             kinds[4 * w] = x.is_b; kinds[4 * w + 1] = blk; kinds[4 * w + 2] = x.g; kinds[4 * w + 3] = (int)trg;
-            mbar_expect_tx(&full[w], (R2C && !x.is_b) ? PIPE_TILE * (uint32_t)sizeof(double) : PIPE_TILE * (uint32_t)sizeof(cd));
+            mbar_expect_tx(&full[w], (R2C && !PACK && !x.is_b) ? PIPE_TILE * (uint32_t)sizeof(double) : PIPE_TILE * (uint32_t)sizeof(cd));
             if (x.is_b) {
                 asm volatile("fence.proxy.async;" ::: "memory");
                 // (RM: a tile of columns k0 .. k0 + C2 - 1 above M/2 loads the rows M - k0 - C2 + 1 .. M - k0 instead: the same bytes count, read backwards)
@@ -467,7 +480,7 @@ fft_fused_kernel(const FusedArgs a, const __grid_constant__ CUtensorMap tm_in, c
                         // extension read backwards, X[c + R t] = conj(H[(R - c) + R (M - 1 - t)]) (column R of the first tile is out of range: zeros)
                         if (q < 2) tma_load_3d(buf + q * QT, &tm_in, 2 * (blk << LC), q * (QT >> LC), (int)tr, &full[w], pol_first);
                         else tma_load_3d(buf + q * QT, &tm_in, 2 * ((1 << LR) - (blk << LC) - (1 << LC) + 1), (q - 2) * (QT >> LC), (int)tr, &full[w], pol_first);
-                    } else if constexpr (R2C)    // real rows: a quarter is 1024 doubles
+                    } else if constexpr (R2C && !PACK)    // real rows: a quarter is 1024 doubles
                         tma_load_2d(reinterpret_cast<double*>(buf) + q * QT, &tm_in, blk << LC, (int)((tr << LM) + q * (QT >> LC)), &full[w], pol_first);
                     else if constexpr (COLS)   // [b][t_hi][t_lo][c]: 16 columns of block cb, t_lo = blk, a quarter of the t_hi range
                         tma_load_4d(buf + q * QT, &tm_in, 32 * (int)(tr & ((1 << a.log_cb) - 1)), blk, q * 64, (int)(tr >> a.log_cb), &full[w], pol_first);
@@ -519,15 +532,23 @@ fft_fused_kernel(const FusedArgs a, const __grid_constant__ CUtensorMap tm_in, c
 #endif
             {
                 const bool half_b = RH && cur_it.is_b;
-                const int blk = half_b ? (int)(cur_it.tau % TPB) : (int)(cur_it.tau & ((1 << LOG_TPT) - 1));
-                const long long trg = half_b ? cur_it.tau / TPB : cur_it.tau >> LOG_TPT;
+                const int ltp = cur_it.is_b ? LOG_TPT : LOG_TPA;
+                const int blk = half_b ? (int)(cur_it.tau % TPB) : (int)(cur_it.tau & ((1 << ltp) - 1));
+                const long long trg = half_b ? cur_it.tau / TPB : cur_it.tau >> ltp;
                 if (!cur_it.is_b) {
                     if (war_seen < war_need) wait_count(war_p, war_need);
                     const long long trl = (long long)(cur_it.g % a.slots) * a.gt + trg;
 #pragma unroll
                     for (int q = 0; q < 4; q++) {
                         if constexpr (COLS) tma_store_4d(&tm_sc, 0, blk, q * 64, (int)trl, buf + q * QT, pol_last);   // [slot][k_hi][t_lo][c16]
-                        else if constexpr (RH || RM) {
+                        else if constexpr (PACK) {
+                            // the unpacked rows k < M/2 of the tile's 2C columns ([k][2C], four quarters of M/8 rows) and, with the last
+                            // quarter, the row k = M/2 from its side buffer (2C contiguous elements of scratch[c + R k])
+                            tma_store_2d(&tm_sc, 2 * (blk << (LC + 1)), (int)((trl << LM) + q * (QT >> (LC + 1))), buf + q * QT, pol_last);
+                            if (q == 3)
+                                bulk_store_hint(const_cast<cd*>(a.scratch) + ((size_t)trl << LOGN) + ((size_t)1 << (LOGN - 1)) + ((size_t)blk << (LC + 1)),
+                                                rowh + w * FUSED_ROWH, (uint32_t)sizeof(cd) << (LC + 1), pol_last);
+                        } else if constexpr (RH || RM) {
                             // rows k < M/2 (two quarters) and the row k = M/2 (C contiguous elements of scratch[c + R k]); the rest is never read
                             if (q < 2) tma_store_2d(&tm_sc, 2 * (blk << LC), (int)((trl << LM) + q * (QT >> LC)), buf + q * QT, pol_last);
                             else if (q == 2)
@@ -631,7 +652,7 @@ fft_fused_kernel(const FusedArgs a, const __grid_constant__ CUtensorMap tm_in, c
             {
                 typedef Geo<LC, LM, 0, 0, RA0, false> G0;
                 constexpr int NB = 16 >> RA0, R0 = 1 << RA0;
-                if constexpr (R2C) {
+                if constexpr (R2C && !PACK) {
                     // the complex results overwrite other threads' real inputs: gather everything first
 #pragma unroll
                     for (int bb = 0; bb < NB; bb++) fused_gather_real<G0, RA0>(&x[bb * R0], sm, G0(t + PIPE_GROUP * bb));
@@ -690,7 +711,34 @@ fft_fused_kernel(const FusedArgs a, const __grid_constant__ CUtensorMap tm_in, c
                 kq = gg.kloc; lo = gg.lo;
             }
             group_sync(g2);   // every gather is done: stage Y[c][k] in place as [k][c], the box the tensor store expects
-            {
+            if constexpr (PACK) {
+                // x[q] = Z[k][lo], k = kq + (q << S): the transform of the complex column lo = the real columns 2 lo, 2 lo + 1. Unpack for k < M/2
+                // (q < 8) with the partner Z[M - k] (q >= 8 of another thread): park the upper half as [k - M/2][C], fetch the partners into
+                // the registers it leaves, then write [k][2C] - rows twice as wide, hence the second barrier before anything is overwritten.
+                constexpr int S = LM - 4;
+                const cd zmid = x[8];                      // Z[M/2] where kq == 0
+#pragma unroll
+                for (int q = 8; q < 16; q++) sm[lo + ((kq + ((q - 8) << S)) << LC)] = x[q];
+                group_sync(g2);
+#pragma unroll
+                for (int q = 0; q < 8; q++) {
+                    const int k = kq + (q << S);
+                    x[8 + q] = k == 0 ? x[0] : sm[lo + (((1 << (LM - 1)) - k) << LC)];   // Z[M - k] sits in row M/2 - k of the parked half
+                }
+                group_sync(g2);
+                cd* p = sm + 2 * lo + (kq << (LC + 1));
+#pragma unroll
+                for (int q = 0; q < 8; q++) {
+                    const cd z = x[q], w = x[8 + q];
+                    p[q << (S + LC + 1)] = make_double2(0.5 * (z.x + w.x), 0.5 * (z.y - w.y));        // (Z + conj W) / 2
+                    p[(q << (S + LC + 1)) + 1] = make_double2(0.5 * (z.y + w.y), 0.5 * (w.x - z.x));  // (Z - conj W) / 2i
+                }
+                if (kq == 0) {   // row k = M/2: Z[M/2] is its own partner
+                    cd* r = rowh + b * FUSED_ROWH + 2 * lo;
+                    r[0] = make_double2(zmid.x, 0.0);
+                    r[1] = make_double2(zmid.y, 0.0);
+                }
+            } else {
                 cd* p = sm + lo + (kq << LC);
 #pragma unroll
                 for (int q = 0; q < 16; q++) p[q << (LM - 4 + LC)] = x[q];

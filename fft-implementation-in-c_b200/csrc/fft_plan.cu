@@ -566,10 +566,11 @@ static int enqueue_fused(fftb200_plan* p, const Pass& ps, const cd* in, cd* out,
         // real input rows of R doubles; output bins 0 .. n/2 - 1 as [b][q < R/2][k] with n/2 + 1 elements per transform
         const cuuint64_t gdim[2] = {(cuuint64_t)1 << lr, (cuuint64_t)nbatch << lm};
         const cuuint64_t gstr[1] = {(cuuint64_t)sizeof(double) << lr};
-        const cuuint32_t box[2] = {(cuuint32_t)1 << (12 - lm), (cuuint32_t)1 << (lm - 2)};
+        // a pass-A tile holds 2C real columns (= C complex columns of adjacent pairs, fft_fused.cuh PACK): a quarter is the box 2C x M/4
+        const cuuint32_t box[2] = {(cuuint32_t)(FUSED_R2C_PACK ? 2 : 1) << (12 - lm), (cuuint32_t)1 << (lm - 2)};
         const cuuint32_t estr[3] = {1, 1, 1};
         CUresult r = enc(&tm[0], CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, (void*)in, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                         CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                         CU_TENSOR_MAP_SWIZZLE_NONE, FUSED_R2C_PACK ? pr : CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled failed (%d) for the real input", (int)r);
         const cuuint64_t odim[3] = {(cuuint64_t)2 << lm, (cuuint64_t)1 << (lr - 1), (cuuint64_t)nbatch};
         const cuuint64_t ostr[2] = {(cuuint64_t)sizeof(cd) << lm, (cuuint64_t)sizeof(cd) * (((cuuint64_t)1 << (L - 1)) + 1)};
@@ -602,7 +603,8 @@ static int enqueue_fused(fftb200_plan* p, const Pass& ps, const cd* in, cd* out,
         void* base = i == 0 ? (void*)in : i == 1 ? (void*)p->fscratch : (void*)out;
         const cuuint64_t gdim[2] = {(cuuint64_t)2 << lcols, (cuuint64_t)ntr << lrows};
         const cuuint64_t gstr[1] = {(cuuint64_t)sizeof(cd) << lcols};
-        const cuuint32_t box[2] = {(cuuint32_t)2 << (12 - lrows), (cuuint32_t)1 << (lrows - 2)};   // a quarter tile: 1024 elements
+        cuuint32_t box[2] = {(cuuint32_t)2 << (12 - lrows), (cuuint32_t)1 << (lrows - 2)};   // a quarter tile: 1024 elements
+        if (r2c == 1 && i == 1 && FUSED_R2C_PACK) { box[0] *= 2; box[1] /= 2; }   // r2c: the unpacked rows k < M/2 of 2C columns, M/8 rows per quarter
         const cuuint32_t estr[2] = {1, 1};
         const CUresult r = enc(&tm[i], CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, base, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                                CU_TENSOR_MAP_SWIZZLE_NONE, i == 0 ? pr : CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -645,7 +647,8 @@ static int enqueue_fused(fftb200_plan* p, const Pass& ps, const cd* in, cd* out,
 #endif
     if (r2c != 1) tm[3] = tm[2];
     const bool herm = r2c == 1 && p->r2c_herm;
-    const long long items = herm ? nbatch * (tpt + tpt / 2 + 1) : 2 * nbatch * tpt;   // Hermitian schedule: pass B on the columns k <= M/2 only
+    const long long tpa = (r2c == 1 && FUSED_R2C_PACK) ? tpt / 2 : tpt;   // packed real input: half the pass-A tiles
+    const long long items = nbatch * (tpa + (herm ? tpt / 2 + 1 : tpt));   // Hermitian schedule: pass B on the columns k <= M/2 only
     const int grid = (int)(items < ps.grid_max ? items : ps.grid_max);
     const void* func = r2c == 1 ? fused_r2c_func(lm, lr, herm) : r2c == 2 ? fused_c2r_func(lm, lr, c2r_half) : cols ? fused_cols_func(inverse) : fused_func(lm, lr, inverse);
     if (!func) return fail("no fused kernel for 2^%d x 2^%d", lm, lr);

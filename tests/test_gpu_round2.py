@@ -276,7 +276,7 @@ def test_plan_follows_its_device(gpu, port, O):
 def test_hermitian_r2c_in_the_fused_kernel(gpu, port, O, n, batch, monkeypatch):
     """r2c of 2^14 .. 2^16 points: pass B of the fused kernel transforms only the columns k <= M/2 and writes the bins of the columns
     M - k as conjugates (fft_fused.cuh, HERM). FFTB200_NO_FUSED_R2C=1 is the promote -> full c2c -> extract plan: the
-    directly computed bins (j mod M <= M/2) are the same arithmetic, bit for bit; the mirrored ones are conj X[j] where the reference has
+    directly computed bins (j mod M <= M/2) are the same arithmetic, to the last bits (pass A packs two real columns into one complex transform); the mirrored ones are conj X[j] where the reference has
     its own X[N - j] - equal only to the accuracy of its twiddle recurrence, which is why sizes above 2^16 keep the full pass B (measured
     mismatch 7.9e-13 at 2^17, 1.8e-12 at 2^18, 7e-12 at 2^20: profiles/r02_real.md). Every size against the oracle at the 1e-12 bar."""
     import torch
@@ -304,7 +304,9 @@ def test_hermitian_r2c_in_the_fused_kernel(gpu, port, O, n, batch, monkeypatch):
         lm = (int(np.log2(n)) + 1) // 2
         k = np.arange(n // 2 + 1) % (1 << lm)
         direct = k <= (1 << lm) // 2
-        assert np.array_equal(y1[:, direct], y2[:, direct])
+        # directly computed bins: the promoted path's arithmetic up to the packed pass A (two real columns per complex transform, exact to
+        # rounding); mirrored bins: conj X[j] for the reference's X[N - j]
+        assert O.rel_l2(y1[:, direct], y2[:, direct]) <= 2e-15
         assert O.rel_l2(y1, y2) <= 5e-13
         # forcing the schedule off gives the full pass B on every column: the promoted path's result to the last bits
         monkeypatch.setenv("FFTB200_R2C_HERMITIAN", "0")
