@@ -60,6 +60,9 @@
 #ifndef FUSED_R2C_PACK
 #define FUSED_R2C_PACK 1
 #endif
+#ifndef FUSED_C2R_HALFCOLS
+#define FUSED_C2R_HALFCOLS 1
+#endif
 
 namespace fftb200 {
 
@@ -202,13 +205,14 @@ __device__ __forceinline__ void bulk_load_hint(void* dst, const void* src, uint3
 struct FusedSched {
     long long nbatch;
     int gt, G, L, log_tpt, a_on, b_on;
-    int log_tpa;   // pass-A tiles per transform (log2): log_tpt, or one less when a tile holds twice the columns (packed real input)
+    int tpa;       // pass-A tiles per transform: 2^log_tpt; half of it when a tile holds twice the columns (packed real input);
+                   // half of it + 1 when only the columns c <= R/2 are transformed (c2r from the half spectrum)
     int tpb;   // pass-B tiles per transform: 2^log_tpt, or 2^(log_tpt - 1) + 1 when only the columns k <= M/2 are transformed (real input)
     __device__ __forceinline__ long long transforms_of(int g) const {
         long long nb = nbatch - (long long)g * gt;
         return nb > gt ? gt : nb;
     }
-    __device__ __forceinline__ long long tiles_of(int g) const { return transforms_of(g) << log_tpa; }   // pass A
+    __device__ __forceinline__ long long tiles_of(int g) const { return transforms_of(g) * tpa; }   // pass A
     __device__ __forceinline__ long long tiles_b(int g) const { return transforms_of(g) * tpb; }        // pass B
     __device__ __forceinline__ long long round_len(int rho) const {
         long long n = 0;
@@ -263,6 +267,25 @@ __device__ __forceinline__ void fused_gather_mirror(cd* x, const cd* sm, const G
     for (int rho = 0; rho < (1 << R); rho++) {
         cd y = sm[base + rho * G::GSTRIDE];
         if (conj) y.y = -y.y;
+        x[bitrev_c<R>(rho)] = y;
+    }
+}
+// c2r, first gather of a pass-B tile whose rows hold the columns c <= R/2 only: Y[c][k] for c > R/2 is conj(w_M^k) conj(Y[R - c][k])
+template <class G, int R, int LR_>
+__device__ __forceinline__ void fused_gather_halfcols(cd* x, const cd* sm, const G& g, const cd wk) {
+    const int base = g.gbase();
+    const int row = base & ~((1 << LR_) - 1), c0 = base & ((1 << LR_) - 1);
+#pragma unroll
+    for (int rho = 0; rho < (1 << R); rho++) {
+        const int c = c0 + rho * G::GSTRIDE;
+        cd y;
+        if (rho < (1 << (R - 1)) || (rho == (1 << (R - 1)) && c0 == 0)) {
+            y = sm[row + c];
+        } else {
+            const cd v = sm[row + (1 << LR_) - c];
+            // conj(wk) * conj(v) = conj(wk * v)
+            y = make_double2(fma(wk.x, v.x, -(wk.y * v.y)), -fma(wk.x, v.y, wk.y * v.x));
+        }
         x[bitrev_c<R>(rho)] = y;
     }
 }
@@ -392,7 +415,12 @@ fft_fused_kernel(const FusedArgs a, const __grid_constant__ CUtensorMap tm_in, c
     // Y[2c'][k] = (Z[k] + conj Z[M - k]) / 2, Y[2c' + 1][k] = (Z[k] - conj Z[M - k]) / 2i for k <= M/2 - half of the pass-A tiles and
     // arithmetic. Pass A uses the accurate tables, so this regrouping is exact to rounding like every other use of them (hybrid rule).
     constexpr bool PACK = R2C && FUSED_R2C_PACK && (RH || RM);
-    constexpr int LOG_TPA = PACK ? LOG_TPT - 1 : LOG_TPT;
+    // HC: c2r from the half spectrum transforms only the columns c <= R/2 in pass A. The input is Hermitian, so for the conjugated input u
+    // the column R - c is u[(R - c) + R (M - 1 - t)] = conj(u[c + R t]) and its transform is Y[R - c][k] = w_M^-k conj(Y[c][k]): pass B
+    // rebuilds the columns above R/2 of its rows in the first gather (one complex multiply with an accurate-table entry per element, exact
+    // to rounding like everything else in pass A's domain). Half + 1 of the pass-A tiles; their scratch stores go with them.
+    constexpr bool HC = CH && FUSED_C2R_HALFCOLS;
+    constexpr int TPA = PACK ? (1 << (LOG_TPT - 1)) : HC ? (1 << (LOG_TPT - 1)) + 1 : (1 << LOG_TPT);
     constexpr int TPB = RH ? (1 << (LOG_TPT - 1)) + 1 : (1 << LOG_TPT);
     constexpr int LC = 12 - LM, LC2 = 12 - LR;          // log2 columns per A tile / k's per B tile
     constexpr int A3 = LM >= 9, B3 = LR >= 9;            // three sub-passes?
@@ -415,10 +443,10 @@ fft_fused_kernel(const FusedArgs a, const __grid_constant__ CUtensorMap tm_in, c
     cd* const rowh = reinterpret_cast<cd*>(smem_raw + FUSED_SMEM - 256) - PIPE_STAGES * FUSED_ROWH;   // [3][64] (r2c, PACK)
 
     FusedSched sch;
-    sch.nbatch = a.nbatch; sch.gt = a.gt; sch.G = a.ngroups; sch.L = a.lag; sch.log_tpt = LOG_TPT; sch.log_tpa = LOG_TPA; sch.tpb = TPB;
+    sch.nbatch = a.nbatch; sch.gt = a.gt; sch.G = a.ngroups; sch.L = a.lag; sch.log_tpt = LOG_TPT; sch.tpa = TPA; sch.tpb = TPB;
     sch.a_on = !(a.debug & 2); sch.b_on = !(a.debug & 1);
     const bool nowait = (a.debug & 7) != 0;
-    const long long total = a.nbatch * (((long long)sch.a_on << LOG_TPA) + (long long)sch.b_on * TPB);
+    const long long total = a.nbatch * ((long long)sch.a_on * TPA + (long long)sch.b_on * TPB);
     const int first = blockIdx.x, stride = gridDim.x;
     const int my_tiles = first < total ? (int)((total - first + stride - 1) / stride) : 0;
 
@@ -454,9 +482,10 @@ fft_fused_kernel(const FusedArgs a, const __grid_constant__ CUtensorMap tm_in, c
         // issue the four quarter loads of tile `x` into the buffer; WAITQ: quarter q only after the store of quarter q has been read
         auto load = [&](const FusedItem& x, auto waitq) {
             const bool half_b = RH && x.is_b;   // pass-B tiles of a real transform are numbered 0 .. TPB - 1 per transform
-            const int ltp = x.is_b ? LOG_TPT : LOG_TPA;
-            const int blk = half_b ? (int)(x.tau % TPB) : (int)(x.tau & ((1 << ltp) - 1));
-            const long long trg = half_b ? x.tau / TPB : x.tau >> ltp;
+            const int per = x.is_b ? TPB : TPA;     // tiles per transform of this pass (compile-time constants: the divisions are cheap)
+            const int blk = (int)(x.tau % per);
+            const long long trg = x.tau / per;
+            (void)half_b;
             kinds[4 * w] = x.is_b; kinds[4 * w + 1] = blk; kinds[4 * w + 2] = x.g; kinds[4 * w + 3] = (int)trg;
             mbar_expect_tx(&full[w], (R2C && !PACK && !x.is_b) ? PIPE_TILE * (uint32_t)sizeof(double) : PIPE_TILE * (uint32_t)sizeof(cd));
             if (x.is_b) {
@@ -532,9 +561,10 @@ fft_fused_kernel(const FusedArgs a, const __grid_constant__ CUtensorMap tm_in, c
 #endif
             {
                 const bool half_b = RH && cur_it.is_b;
-                const int ltp = cur_it.is_b ? LOG_TPT : LOG_TPA;
-                const int blk = half_b ? (int)(cur_it.tau % TPB) : (int)(cur_it.tau & ((1 << ltp) - 1));
-                const long long trg = half_b ? cur_it.tau / TPB : cur_it.tau >> ltp;
+                const int per = cur_it.is_b ? TPB : TPA;
+                const int blk = (int)(cur_it.tau % per);
+                const long long trg = cur_it.tau / per;
+                (void)half_b;
                 if (!cur_it.is_b) {
                     if (war_seen < war_need) wait_count(war_p, war_need);
                     const long long trl = (long long)(cur_it.g % a.slots) * a.gt + trg;
@@ -791,7 +821,17 @@ fft_fused_kernel(const FusedArgs a, const __grid_constant__ CUtensorMap tm_in, c
             {
                 typedef Geo<0, LR, LC2, 0, RB0, false> G0;
                 constexpr int NB = 16 >> RB0, R0 = 1 << RB0;
-                if constexpr (RM) {
+                if constexpr (HC) {
+                    // columns c <= R/2 as stored; c > R/2 rebuilt as w_M^-k conj(Y[R - c][k]) from the same row (k = the tile's row)
+#pragma unroll
+                    for (int bb = 0; bb < NB; bb++) {
+                        const G0 g(t + PIPE_GROUP * bb);
+                        const int k = (kb << LC2) + g.hi;
+                        cd wk = __ldg(a.acc + ((1 << (LM - 1)) - 1 + (k & ((1 << (LM - 1)) - 1))));   // w_M^(k mod M/2); w_M^(k + M/2) = -w_M^k
+                        if (k >> (LM - 1)) { wk.x = -wk.x; wk.y = -wk.y; }
+                        fused_gather_halfcols<G0, RB0, LR>(&x[bb * R0], sm, g, wk);
+                    }
+                } else if constexpr (RM) {
                     // 0: the tile's own rows; 1: the rows M - k, backwards and conjugated; 2: the tile that starts at k = M/2 (its first row is its own)
                     const int mode = kb < (1 << (LOG_TPT - 1)) ? 0 : kb == (1 << (LOG_TPT - 1)) ? 2 : 1;
 #pragma unroll

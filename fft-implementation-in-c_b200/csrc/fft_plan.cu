@@ -541,7 +541,8 @@ static int enqueue_fused(fftb200_plan* p, const Pass& ps, const cd* in, cd* out,
         p->fscratch = (cd*)fftb200_malloc(sizeof(cd) * need);
         if (!p->fscratch) return -1;
         p->fscratch_elems = need;
-        // r2c: the last pass-B tile of a transform reads rows above k = M/2 that pass A never stores (their results are dropped)
+        // r2c (Hermitian schedule): the last pass-B tile of a transform reads rows above k = M/2 that pass A never stores (their results are
+        // dropped); c2r from the half spectrum: pass-B tiles load whole rows of which only the columns c <= R/2 (+ one tile) are ever written
         CU(cudaMemsetAsync(p->fscratch, 0, sizeof(cd) * need, p->stream));
     }
     const size_t nflags = (size_t)(2 * G + 1);
@@ -647,7 +648,8 @@ static int enqueue_fused(fftb200_plan* p, const Pass& ps, const cd* in, cd* out,
 #endif
     if (r2c != 1) tm[3] = tm[2];
     const bool herm = r2c == 1 && p->r2c_herm;
-    const long long tpa = (r2c == 1 && FUSED_R2C_PACK) ? tpt / 2 : tpt;   // packed real input: half the pass-A tiles
+    // packed real input: half the pass-A tiles; c2r from the half spectrum: the columns c <= R/2 only
+    const long long tpa = (r2c == 1 && FUSED_R2C_PACK) ? tpt / 2 : (c2r_half && FUSED_C2R_HALFCOLS) ? tpt / 2 + 1 : tpt;
     const long long items = nbatch * (tpa + (herm ? tpt / 2 + 1 : tpt));   // Hermitian schedule: pass B on the columns k <= M/2 only
     const int grid = (int)(items < ps.grid_max ? items : ps.grid_max);
     const void* func = r2c == 1 ? fused_r2c_func(lm, lr, herm) : r2c == 2 ? fused_c2r_func(lm, lr, c2r_half) : cols ? fused_cols_func(inverse) : fused_func(lm, lr, inverse);

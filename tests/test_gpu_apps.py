@@ -97,7 +97,7 @@ def test_c2r_fused_kernel_stores_real_parts(gpu, port, O, n, batch, monkeypatch)
     y2, d2 = run()
     monkeypatch.delenv("FFTB200_NO_FUSED_C2R")
     assert b"+ real parts" in d2
-    assert np.array_equal(y1, y2)
+    assert O.rel_l2(y1, y2) <= 2e-15   # (the fused path reads the half spectrum and transforms half of the pass-A columns: same values to the last bits)
     rows = sorted({0, batch - 1})
     assert O.rel_l2(y1[rows], np.stack([port.c2r(half[r], n) for r in rows])) <= TOL
 

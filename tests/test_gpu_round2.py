@@ -201,8 +201,9 @@ def test_c2r_in_place_where_it_is_allowed(gpu, port, O):
 def test_c2r_reads_the_half_spectrum_inside_the_fused_kernel(gpu, port, O, n, batch, monkeypatch):
     """c2r of 2^14 .. 2^20 points: the fused inverse kernel loads the half spectrum itself - each pass-A tile is two boxes, its own columns and
     the mirrored ones, and the first gather reads the mirrored half backwards (fft_fused.cuh, C2R + HERM). FFTB200_C2R_HERMITIAN=0 keeps the
-    separate c2r_expand pass over a full-length work array: the same values through the same arithmetic, so the outputs are identical bit for
-    bit (unlike r2c, nothing is approximated here: the extension X[N - j] = conj X[j] IS the definition of c2r). Rows against the oracle."""
+    separate c2r_expand pass over a full-length work array. Nothing is approximated (the extension X[N - j] = conj X[j] IS the definition of
+    c2r); pass A transforms only the columns c <= R/2 and pass B rebuilds the rest with one accurate-table multiply, so the two paths agree to
+    the last bits. Rows against the oracle."""
     import torch
     L = gpu.lib
     x = port.fill(83, 0, n * batch).real.copy().reshape(batch, n)
@@ -226,7 +227,8 @@ def test_c2r_reads_the_half_spectrum_inside_the_fused_kernel(gpu, port, O, n, ba
     monkeypatch.delenv("FFTB200_C2R_HERMITIAN")
     assert "hermitian extension" in d2, d2
     assert np.isfinite(y1).all()
-    assert np.array_equal(y1, y2)
+    # pass A runs on the columns c <= R/2 only; pass B rebuilds the others as w_M^-k conj(Y[R - c][k]) - one more rounding on half of its inputs
+    assert O.rel_l2(y1, y2) <= 2e-15
     rows = sorted({0, batch - 1})
     assert O.rel_l2(y1[rows], np.stack([port.c2r(half[r], n) for r in rows])) <= TOL
 
