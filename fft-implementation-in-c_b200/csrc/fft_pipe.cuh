@@ -55,7 +55,8 @@ constexpr int PIPE_TILE = 4096;              // complex elements per tile
 constexpr int PIPE_STAGES = 3;               // ring depth
 constexpr int PIPE_GROUP = 256;              // threads per group
 constexpr int PIPE_TW1 = 16 * 8;             // shared copy of the middle sub-pass twiddles: [kloc][8]
-constexpr size_t PIPE_SMEM = (size_t)PIPE_STAGES * PIPE_TILE * sizeof(cd) + PIPE_TW1 * sizeof(cd) + 64;
+constexpr int PIPE_SLOT_C2R = PIPE_TILE + 16;   // c2r: a ring slot holds 2 NT half spectra of N/2 + 1 bins = 4096 + 2 NT elements
+constexpr size_t PIPE_SMEM = (size_t)PIPE_STAGES * PIPE_SLOT_C2R * sizeof(cd) + PIPE_TW1 * sizeof(cd) + 64;
 
 __device__ __forceinline__ int pipe_swz(int idx) { return idx ^ ((idx >> 4) & 7); }
 
@@ -126,10 +127,14 @@ __device__ __forceinline__ cd cmulc(const cd a, const double c, const double d) 
     return make_double2(fma(a.x, c, -(a.y * d)), fma(a.x, d, a.y * c));
 }
 
-// REAL = PIPE_R2C: the tile holds 4096 reals (promoted while gathering, fft_auto.c:394-397) and only the bins 0 .. N/2 are
-// stored, N/2 + 1 per transform (fft_auto.h:89-97) - the reference's promote-then-c2c reading of fft_plan_r2c_1d without
-// the promotion and extraction passes. REAL = PIPE_C2R (inverse only): the tile holds N/2 + 1 bins per transform, the
-// Hermitian half X[N - i] = conj(X[i]) is rebuilt while gathering and the real parts are stored (fft_auto.h:99-107).
+// REAL = PIPE_R2C: the tile holds 8192 reals = 2 NT real transforms; rows 2j and 2j + 1 are transformed TOGETHER as the complex
+// sequence z = x_a + i x_b (every stage here uses the accurate conjugate-symmetric tables, so this regrouping is exact to rounding)
+// and separated at the end, X_a[k] = (Z[k] + conj Z[N - k]) / 2, X_b[k] = (Z[k] - conj Z[N - k]) / 2i - the partners Z[N - k] sit in
+// another thread of the same transform and are traded through the tile. Only the bins 0 .. N/2 are stored, N/2 + 1 per transform
+// (fft_auto.h:89-97): the reference's promote-then-c2c reading of fft_plan_r2c_1d (fft_auto.c:394-397) at half the arithmetic and
+// without the promotion and extraction passes. REAL = PIPE_C2R (inverse only): the slot holds N/2 + 1 bins of 2 NT transforms; rows 2j
+// and 2j + 1 enter ONE inverse transform as Z = X_a + i X_b (Hermitian halves rebuilt while gathering), whose real and imaginary
+// parts are the two real results (fft_auto.h:99-107).
 // REAL = PIPE_BLUE_FWD / PIPE_BLUE_INV: the two transforms of Bluestein's algorithm for padded lengths N = 512 .. 4096 with the
 // elementwise steps riding on them: FWD reads the caller's n-point rows, multiplies by conj(chirp) and zero-pads while gathering,
 // and multiplies the spectrum by FB before storing it; INV (inverse c2c, 1/N) multiplies by conj(chirp) * y_scale and stores the
@@ -142,13 +147,16 @@ __global__ void __launch_bounds__(2 * PIPE_GROUP, 1) fft_pipe_kernel(const PipeA
     static_assert(REAL == PIPE_C2C || ((REAL == PIPE_R2C || REAL == PIPE_BLUE_FWD) && !INV) || ((REAL == PIPE_C2R || REAL == PIPE_BLUE_INV) && INV),
                   "r2c and Bluestein's first transform are forward, c2r and its second inverse");
     constexpr int NH = (1 << LOGN) / 2 + 1;   // bins per transform of a half spectrum
-    constexpr int N = 1 << LOGN, NT = PIPE_TILE / N;  // transforms per tile
+    constexpr int N = 1 << LOGN, NT = PIPE_TILE / N;  // (complex) transforms per tile
+    constexpr bool PAIR = REAL == PIPE_R2C || REAL == PIPE_C2R;   // two real transforms per complex transform
+    constexpr int NTR = PAIR ? 2 * NT : NT;                        // caller's transforms per tile
+    constexpr int SLOT = REAL == PIPE_C2R ? PIPE_SLOT_C2R : PIPE_TILE;
     constexpr int LR0 = LOGN - 8, R0 = 1 << LR0, NB0 = 16 / R0;
     constexpr int LN16 = LOGN - 4;                    // log2 (N / 16)
 
     extern __shared__ __align__(128) unsigned char smem_raw[];
     cd* const bufs = reinterpret_cast<cd*>(smem_raw);
-    cd* const tw1s = bufs + (size_t)PIPE_STAGES * PIPE_TILE;
+    cd* const tw1s = bufs + (size_t)PIPE_STAGES * PIPE_SLOT_C2R;
     uint64_t* const full = reinterpret_cast<uint64_t*>(tw1s + PIPE_TW1);
 
     const int g = threadIdx.x / PIPE_GROUP, t = threadIdx.x % PIPE_GROUP;
@@ -163,14 +171,14 @@ __global__ void __launch_bounds__(2 * PIPE_GROUP, 1) fft_pipe_kernel(const PipeA
     // parity (round >> 1) & 1): all phases of one barrier are waited for by the same group, in program order.
     auto issue = [&](int k, int b, uint32_t rnd) {  // one thread: start the load of this CTA's k-th tile into buffer b
         const long long tile = first + (long long)k * stride;
-        long long nvalid = a.batch - tile * NT;
-        if (nvalid > NT) nvalid = NT;
+        long long nvalid = a.batch - tile * NTR;
+        if (nvalid > NTR) nvalid = NTR;
         const uint32_t per = REAL == PIPE_R2C ? N * (uint32_t)sizeof(double) : REAL == PIPE_C2R ? NH * (uint32_t)sizeof(cd)
                            : REAL == PIPE_BLUE_FWD ? (uint32_t)a.n_user * (uint32_t)sizeof(cd) : N * (uint32_t)sizeof(cd);
         const uint32_t bytes = (uint32_t)nvalid * per;
         uint64_t* const bar = &full[b + PIPE_STAGES * (rnd & 1)];
         mbar_expect_tx(bar, bytes);
-        bulk_load(bufs + (size_t)b * PIPE_TILE, reinterpret_cast<const char*>(a.in) + (size_t)tile * NT * per, bytes, bar);
+        bulk_load(bufs + (size_t)b * SLOT, reinterpret_cast<const char*>(a.in) + (size_t)tile * NTR * per, bytes, bar);
     };
 
     if (threadIdx.x == 0) {
@@ -216,21 +224,30 @@ __global__ void __launch_bounds__(2 * PIPE_GROUP, 1) fft_pipe_kernel(const PipeA
     int b = g % PIPE_STAGES;   // ring slot of tile k
     uint32_t round = 0;        // k / PIPE_STAGES
     for (int k = g; k < my_tiles; k += 2) {
-        cd* const sm = bufs + (size_t)b * PIPE_TILE;
+        cd* const sm = bufs + (size_t)b * SLOT;
         mbar_wait_bounded(&full[b + PIPE_STAGES * (round & 1)], (round >> 1) & 1);
         cd x[16];
+        const long long tile_k = first + (long long)k * stride;
+        const int rows_left = (int)(a.batch - tile_k * NTR < NTR ? a.batch - tile_k * NTR : NTR);   // caller's transforms in this tile; a pair's
+                                                                                                    // second row beyond them reads as zeros
         // ---- sub-pass 0: radix R0, exact constants, in place (each thread owns idx = t + 256 e) ----
 #pragma unroll
         for (int e = 0; e < 16; e++) {
             cd y;
             if constexpr (REAL == PIPE_R2C) {
-                y = make_double2(reinterpret_cast<const double*>(sm)[t + 256 * e], 0.0);
+                // z = x_a + i x_b of the rows 2 jj, 2 jj + 1 (jj == j: t + 256 e stays inside the thread's transform)
+                const int idx = t + 256 * e, jj = idx >> LOGN, i = idx & (N - 1);
+                const double* sr = reinterpret_cast<const double*>(sm) + 2 * jj * N + i;
+                y = make_double2(sr[0], 2 * jj + 1 < rows_left ? sr[N] : 0.0);
             } else if constexpr (REAL == PIPE_C2R) {
-                // element i of transform jj: bin i for i <= N/2, conj(bin N - i) above; conjugated once more for the inverse
+                // Z = X_a + i X_b, X[i] = bin i for i <= N/2 and conj(bin N - i) above; conjugated for the inverse
                 const int idx = t + 256 * e, jj = idx >> LOGN, i = idx & (N - 1);
                 const bool up = i > N / 2;
-                y = sm[jj * NH + (up ? N - i : i)];
-                if (!up) y.y = -y.y;
+                const cd* sp = sm + 2 * jj * NH + (up ? N - i : i);
+                const cd A = sp[0];
+                cd B = sp[NH];
+                if (2 * jj + 1 >= rows_left) B = make_double2(0.0, 0.0);
+                y = up ? make_double2(A.x + B.y, A.y - B.x) : make_double2(A.x - B.y, -A.y - B.x);
             } else if constexpr (REAL == PIPE_BLUE_FWD) {
                 // a = x * conj(chirp), zero-padded from n to N (bluestein.c:107-109)
                 const int idx = t + 256 * e, jj = idx >> LOGN, i = idx & (N - 1);
@@ -276,8 +293,8 @@ __global__ void __launch_bounds__(2 * PIPE_GROUP, 1) fft_pipe_kernel(const PipeA
             wa = __ldg(a.tab + (v - 1) + (1 << LN16)); wb = __ldg(a.tab + (v - 1) + (2 << LN16));
             wc = __ldg(a.tab + (v - 1) + (4 << LN16)); wd = __ldg(a.tab + (v - 1) + (8 << LN16));
         }
-        group_sync(g);  // the buffer is free: refill it with this CTA's tile k + 3
-        if (t == 0 && k + PIPE_STAGES < my_tiles) {
+        group_sync(g);  // the buffer is free: refill it with this CTA's tile k + 3 (r2c: after the partner exchange below)
+        if (REAL != PIPE_R2C && t == 0 && k + PIPE_STAGES < my_tiles) {
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             issue(k + PIPE_STAGES, b, round + 1);
         }
@@ -295,18 +312,47 @@ __global__ void __launch_bounds__(2 * PIPE_GROUP, 1) fft_pipe_kernel(const PipeA
             const long long tile = first + (long long)k * stride;
             const bool valid = tile * NT + j < a.batch;
             if constexpr (REAL == PIPE_R2C) {
-                // bins k = v + (q << LN16) <= N/2: q < 8, and the Nyquist bin (q = 8, v = 0)
-                cd* p = a.out + (size_t)(tile * NT + j) * NH + v;
-                if (valid) {
+                // x[q] = Z[k], k = v + (q << LN16). The bins k < N/2 (q < 8) need the partner Z[N - k], held as q' = 15 - q by thread
+                // N/16 - v of the same transform: park the upper half in natural order, fetch the partners into the registers it leaves
+                const cd zmid = x[8];                      // Z[N/2] where v == 0
 #pragma unroll
-                    for (int q = 0; q < 8; q++) p[q << LN16] = x[q];
-                    if (v == 0) p[8 << LN16] = x[8];
+                for (int q = 8; q < 16; q++) sm[wr1 + (q << LN16)] = x[q];
+                group_sync(g);
+#pragma unroll
+                for (int q = 0; q < 8; q++) {
+                    const int kk = v + (q << LN16);
+                    x[8 + q] = kk == 0 ? x[0] : sm[j * N + N - kk];
+                }
+                group_sync(g);  // now the buffer is free
+                if (t == 0 && k + PIPE_STAGES < my_tiles) {
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    issue(k + PIPE_STAGES, b, round + 1);
+                }
+                // X_a = (Z + conj W) / 2 -> row 2j, X_b = (Z - conj W) / 2i -> row 2j + 1; bins 0 .. N/2 - 1, and the Nyquist bins (v == 0)
+                const long long row = tile * NTR + 2 * j;
+                cd* pa = a.out + (size_t)row * NH + v;
+                cd* pb = pa + NH;
+                const bool va = row < a.batch, vb = row + 1 < a.batch;
+#pragma unroll
+                for (int q = 0; q < 8; q++) {
+                    const cd z = x[q], w = x[8 + q];
+                    if (va) pa[q << LN16] = make_double2(0.5 * (z.x + w.x), 0.5 * (z.y - w.y));
+                    if (vb) pb[q << LN16] = make_double2(0.5 * (z.y + w.y), 0.5 * (w.x - z.x));
+                }
+                if (v == 0) {
+                    if (va) pa[8 << LN16] = make_double2(zmid.x, 0.0);
+                    if (vb) pb[8 << LN16] = make_double2(zmid.y, 0.0);
                 }
             } else if constexpr (REAL == PIPE_C2R) {
-                double* p = reinterpret_cast<double*>(a.out) + tile * PIPE_TILE + wr1;
-                if (valid) {
+                // the inverse of Z = X_a + i X_b is x_a + i x_b (conjugated and scaled here): real part -> row 2j, imaginary part -> row 2j + 1
+                const long long row = tile * NTR + 2 * j;
+                double* pa = reinterpret_cast<double*>(a.out) + (size_t)row * N + v;
+                double* pb = pa + N;
+                const bool va = row < a.batch, vb = row + 1 < a.batch;
 #pragma unroll
-                    for (int q = 0; q < 16; q++) p[q << LN16] = x[q].x * sc;
+                for (int q = 0; q < 16; q++) {
+                    if (va) pa[q << LN16] = x[q].x * sc;
+                    if (vb) pb[q << LN16] = -(x[q].y * sc);
                 }
             } else if constexpr (REAL == PIPE_BLUE_FWD) {
                 // A * FB (bluestein.c:124-131); factors fetched four at a time ahead of the stores they feed

@@ -1240,7 +1240,7 @@ static int exec_range(fftb200_plan* p, const void* d_in, void* d_out, long long 
     if (p->pipe_real) {
         if (nbatch <= 0) return 0;
         const Pass& ps = p->passes[0];
-        const long long ntiles = pass_tiles(ps, nbatch);
+        const long long ntiles = (nbatch + 2 * ps.nt - 1) / (2 * ps.nt);   // two real transforms per complex transform: 2 nt rows per tile
         PipeArgs pa;
         pa.in = (const cd*)d_in; pa.out = (cd*)d_out; pa.tab = p->acc;
         pa.ntiles = ntiles; pa.batch = nbatch;

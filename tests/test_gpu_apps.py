@@ -39,11 +39,12 @@ def test_c2r_batched_engine_plan(gpu, port, O, n, batch):
     L.fftb200_plan_destroy(plan)
 
 
-@pytest.mark.parametrize("n,batch", [(512, 1), (512, 1187), (1024, 5), (2048, 300), (4096, 1), (4096, 301)])
+@pytest.mark.parametrize("n,batch", [(512, 1), (512, 2), (512, 1187), (1024, 5), (1024, 16), (2048, 300), (4096, 1), (4096, 2), (4096, 301)])
 def test_real_variants_of_the_pipe_kernel(gpu, port, O, n, batch, monkeypatch):
     """Batched r2c / c2r of 512 .. 4096 points run in fft_pipe_kernel's real variants (reals / half spectra read and written by
     the kernel itself); FFTB200_NO_PIPE_REAL=1 is promote - c2c - extract (r2c) and extend - inverse c2c - real parts (c2r).
-    The arithmetic is the same: bit-identical, and equal to the oracle. Batches ragged against the 4096-point tiles."""
+    Same operators (two real transforms share one complex transform in the kernel: exact to rounding), equal to the oracle. Batches ragged
+    against the tiles of 8192 reals, odd batches leave a pair half empty."""
     import torch
     L = gpu.lib
     x = port.fill(75, 0, n * batch).real.copy().reshape(batch, n)
@@ -67,7 +68,10 @@ def test_real_variants_of_the_pipe_kernel(gpu, port, O, n, batch, monkeypatch):
     h2, y2, d2 = run()
     monkeypatch.delenv("FFTB200_NO_PIPE_REAL")
     assert b"hermitian extension" in d2
-    assert np.array_equal(h1, h2) and np.array_equal(y1, y2)
+    # the kernel transforms two real rows as ONE complex transform (z = x_a + i x_b, separated at the end; two half spectra packed as
+    # X_a + i X_b on the way back): exact to rounding, so the two paths agree to the last bits - and the c2r input is the r2c output of
+    # each path, hence the looser second bound
+    assert O.rel_l2(h1, h2) <= 2e-15 and O.rel_l2(y1, y2) <= 4e-15
     rows = sorted({0, batch // 2, batch - 1})
     assert O.rel_l2(h1[rows], np.stack([port.r2c(x[r]) for r in rows])) <= TOL
     assert O.rel_l2(y1, x) <= TOL
