@@ -1152,7 +1152,7 @@ __global__ void peer_barrier_kernel(unsigned long long* const* flags, int world,
         unsigned long long v;
         asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(mine) : "memory");
         if (v >= epoch) break;
-        if (it > (1LL << 31)) __trap();   // a rank that never arrives fails the launch instead of hanging the GPU for good
+        if (it > (1LL << 28)) __trap();   // ~1 min: a rank that never arrives fails the launch instead of hanging the GPU for good
         __nanosleep(200);
     }
 }
