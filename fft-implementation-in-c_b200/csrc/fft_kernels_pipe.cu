@@ -2,6 +2,7 @@
 #include "fft_catalog.h"
 #include "fft_pipe.cuh"
 #include "fft_pipe13.cuh"
+#include "fft_pipe13t.cuh"
 namespace fftb200 {
 
 template <int LOGN, bool INV>
@@ -60,6 +61,15 @@ const void* pipe13_func(int inverse) {
 cudaError_t launch_pipe13(const PipeArgs& a, int grid, cudaStream_t s) {
     if (a.inverse) fft_pipe13_kernel<true><<<grid, 2 * PIPE_GROUP, PIPE_SMEM, s>>>(a);
     else fft_pipe13_kernel<false><<<grid, 2 * PIPE_GROUP, PIPE_SMEM, s>>>(a);
+    return cudaGetLastError();
+}
+// N = 8192 with tensor memory as the parking space (fft_pipe13t.cuh)
+const void* pipe13t_func(int inverse) {
+    return inverse ? (const void*)fft_pipe13t_kernel<true> : (const void*)fft_pipe13t_kernel<false>;
+}
+cudaError_t launch_pipe13t(const PipeArgs& a, int grid, cudaStream_t s) {
+    if (a.inverse) fft_pipe13t_kernel<true><<<grid, 2 * PIPE_GROUP, PIPE_SMEM, s>>>(a);
+    else fft_pipe13t_kernel<false><<<grid, 2 * PIPE_GROUP, PIPE_SMEM, s>>>(a);
     return cudaGetLastError();
 }
 }  // namespace fftb200

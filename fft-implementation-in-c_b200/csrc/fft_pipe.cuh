@@ -7,9 +7,11 @@
 // Structure (one CTA per SM, 512 threads = two groups of 256):
 //   * a tile is 4096 consecutive complex doubles of the batch buffer = 4096/N whole transforms;
 //   * three 64 KB shared-memory buffers form a ring. One thread issues a 1-D bulk async copy (TMA,
-//     cp.async.bulk + mbarrier complete_tx) for tile k+3 as soon as tile k has left its buffer, so two
+//     cp.async.bulk + mbarrier complete_tx) for the CTA's next tile as soon as a tile has left its buffer, so two
 //     tiles (128 KB) are always in flight per SM while a third is being computed: HBM never waits for
 //     the FP64 pipe and the other way round;
+//   * tiles are handed out on demand from a global counter (round 2, "Tile order" in the kernel): the SMs of a B200 do not
+//     all move data at the same rate, and a fixed tile-to-CTA assignment leaves 5-8 % of the HBM rate unused;
 //   * the two thread groups work on alternate tiles and meet only through the ring, so one group's
 //     shared-memory exchange overlaps the other group's butterflies;
 //   * a thread holds 16 points in registers. Three sub-passes (radix N/256, 16, 16) regroup the
@@ -24,7 +26,7 @@
 // as the reference-recurrence table), which has the symmetry w[q + m/4] = -i * w[q]; only 8 of the 15
 // twiddles of a radix-16 butterfly are needed, the other 7 are free sign/swap variants. The middle
 // sub-pass reads its 8 from a 2 KB shared table; the last sub-pass's twiddles depend only on the thread
-// index: w^8, w^4, w^2, w stay in registers for the whole kernel, the other four are w^2 * W8 and
+// index: w^8, w^4, w^2, w are re-read per tile (L1 hits), the other four are w^2 * W8 and
 // w * {W16, W8, W16^3}, rebuilt per tile (16 FP64 instructions).
 //
 // Measured alternatives (same box A/B, N = 4096 x 65536, ms): this form 1.31-1.32; all 8 last-pass twiddles
@@ -49,6 +51,9 @@ struct PipeArgs {
     const cd* fb;
     int n_user;
     double y_scale;    // 1/n for the inverse direction of the caller's transform, else 1
+    // dynamic tile hand-out (see "Tile order" in fft_pipe_kernel): sched[0] = tiles taken beyond the first three of every CTA,
+    // sched[1] = CTAs that have finished; both are zero between launches.
+    unsigned int* sched;
 };
 
 constexpr int PIPE_TILE = 4096;              // complex elements per tile
@@ -56,7 +61,7 @@ constexpr int PIPE_STAGES = 3;               // ring depth
 constexpr int PIPE_GROUP = 256;              // threads per group
 constexpr int PIPE_TW1 = 16 * 8;             // shared copy of the middle sub-pass twiddles: [kloc][8]
 constexpr int PIPE_SLOT_C2R = PIPE_TILE + 16;   // c2r: a ring slot holds 2 NT half spectra of N/2 + 1 bins = 4096 + 2 NT elements
-constexpr size_t PIPE_SMEM = (size_t)PIPE_STAGES * PIPE_SLOT_C2R * sizeof(cd) + PIPE_TW1 * sizeof(cd) + 64;
+constexpr size_t PIPE_SMEM = (size_t)PIPE_STAGES * PIPE_SLOT_C2R * sizeof(cd) + PIPE_TW1 * sizeof(cd) + 128;   // + barriers, tile numbers
 
 __device__ __forceinline__ int pipe_swz(int idx) { return idx ^ ((idx >> 4) & 7); }
 
@@ -90,6 +95,9 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)_
 
 __device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
@@ -159,9 +167,27 @@ __global__ void __launch_bounds__(2 * PIPE_GROUP, 1) fft_pipe_kernel(const PipeA
     cd* const tw1s = bufs + (size_t)PIPE_STAGES * PIPE_SLOT_C2R;
     uint64_t* const full = reinterpret_cast<uint64_t*>(tw1s + PIPE_TW1);
 
+    int* const tile_of = reinterpret_cast<int*>(full + 2 * PIPE_STAGES);   // [6]: the tile a barrier's current phase stands for, -1 = no more
+    int* const next_of = tile_of + 2 * PIPE_STAGES;                        // [2]: the tile a group will load next
+    int* const cur_of = next_of + 2;                                       // [2][3]: the tile a group works on (its own copy: tile_of[] is
+                                                                           // rewritten as soon as the slot three ahead is loaded or closed)
+
     const int g = threadIdx.x / PIPE_GROUP, t = threadIdx.x % PIPE_GROUP;
     const int first = blockIdx.x, stride = gridDim.x;
-    const int my_tiles = first < a.ntiles ? (int)((a.ntiles - first + stride - 1) / stride) : 0;
+
+    // Tile order. The SMs of this chip do not move data at the same rate (a plain copy with a fixed tile-to-CTA assignment reaches
+    // 6.0-6.4 TB/s, the same copy with tiles handed out on demand 6.9-7.0: tools/copybench.cu, profiles/r02_microbench.md), so a CTA
+    // takes its first three tiles by position (CTA + k * grid: nothing to wait for at start-up) and every later one from a global
+    // counter: ring slot s of the CTA (buffer s % 3, group s % 2) carries whatever tile its loader was handed, the number travels in
+    // shared memory next to the barrier, and a number past the end (-1) tells the group that waits for the slot to stop - after it
+    // has passed the same message to the slot three ahead, whose loader it would have been. The counter is read one tile ahead
+    // (after a tile's results have left, when no butterfly registers are live) so that its latency stays off the critical path,
+    // and the last CTA to finish sets it back to zero for the next launch.
+    // (tile numbers fit 32 bits: 2^31 tiles of 64 KB are more than any memory holds; clamped so that they never wrap)
+    auto take = [&]() -> int {   // the tile of this group's next load
+        const unsigned v = 3u * gridDim.x + atomicAdd(a.sched, 1u);
+        return v < 0x7fffffffu ? (int)v : 0x7fffffff;
+    };
 
     // Barriers: buffer b is filled for tiles b, b + 3, b + 6, ... which the two groups consume alternately, and the load
     // of tile k + 3 is issued by the group that consumed tile k - not by the group that will wait for it. With ONE barrier
@@ -169,14 +195,19 @@ __global__ void __launch_bounds__(2 * PIPE_GROUP, 1) fft_pipe_kernel(const PipeA
     // parity wait then passes on the phase before: stale data, a second expect_tx in the same phase and a launch failure;
     // seen on the B200 about once per 10^7 tiles). So each buffer has TWO barriers used in turn (bar = b + 3 * (round & 1),
     // parity (round >> 1) & 1): all phases of one barrier are waited for by the same group, in program order.
-    auto issue = [&](int k, int b, uint32_t rnd) {  // one thread: start the load of this CTA's k-th tile into buffer b
-        const long long tile = first + (long long)k * stride;
-        long long nvalid = a.batch - tile * NTR;
+    auto issue = [&](int tile, int b, uint32_t rnd) {  // one thread: start the load of `tile` into buffer b
+        uint64_t* const bar = &full[b + PIPE_STAGES * (rnd & 1)];
+        if (tile >= a.ntiles) {   // nothing left: complete the phase without data
+            tile_of[b + PIPE_STAGES * (rnd & 1)] = -1;
+            mbar_arrive(bar);
+            return;
+        }
+        tile_of[b + PIPE_STAGES * (rnd & 1)] = tile;
+        long long nvalid = a.batch - (long long)tile * NTR;
         if (nvalid > NTR) nvalid = NTR;
         const uint32_t per = REAL == PIPE_R2C ? N * (uint32_t)sizeof(double) : REAL == PIPE_C2R ? NH * (uint32_t)sizeof(cd)
                            : REAL == PIPE_BLUE_FWD ? (uint32_t)a.n_user * (uint32_t)sizeof(cd) : N * (uint32_t)sizeof(cd);
         const uint32_t bytes = (uint32_t)nvalid * per;
-        uint64_t* const bar = &full[b + PIPE_STAGES * (rnd & 1)];
         mbar_expect_tx(bar, bytes);
         bulk_load(bufs + (size_t)b * SLOT, reinterpret_cast<const char*>(a.in) + (size_t)tile * NTR * per, bytes, bar);
     };
@@ -196,39 +227,48 @@ __global__ void __launch_bounds__(2 * PIPE_GROUP, 1) fft_pipe_kernel(const PipeA
     }
     __syncthreads();
     if (threadIdx.x == 0) {
-        for (int k = 0; k < PIPE_STAGES && k < my_tiles; k++) issue(k, k, 0);
+        for (int k = 0; k < PIPE_STAGES; k++) issue((long long)first + (long long)k * stride < a.ntiles ? first + k * stride : 0x7fffffff, k, 0);
     }
+    int ahead = 0;   // thread 0 of a group: the tile its next load will fetch
+    if (t == 0) ahead = take();
 
     // thread-constant butterfly coordinates of the two radix-16 sub-passes
     const int j = t >> LN16;              // transform within the tile
     const int v = t & ((1 << LN16) - 1);  // butterfly within the transform
     const int cp = v & 15, kloc1 = v >> 4;
     // last sub-pass: stage (LN16 + s), position kappa = v -> tab[(h << LN16) + v - 1]. The four powers
-    // w^8, w^4, w^2, w (h = 1, 2, 4, 8) stay in registers; h = 5, 9, 10, 11 are w^2 * W8, w * W16, w * W8,
-    // w * W16^3, rebuilt per tile (16 FP64 instructions) to keep the register file free of spills.
-    // N = 4096 keeps them in registers for the whole kernel (HBM-bound, 1.31 vs 1.36 ms); the smaller sizes are bound by the
-    // butterflies and exchanges and gain from the eight registers: they re-read the four entries per tile (L1 hits):
-    // same box, 2^28 points: N = 512 1.41 -> 1.35, N = 1024 1.46 -> 1.33, N = 2048 1.42 -> 1.30 ms
-    constexpr bool TW_REGS = LOGN == 12 && REAL == PIPE_C2C;   // (the real / Bluestein variants of N = 4096 are not HBM-bound either)
-    cd wa0, wb0, wc0, wd0;
-    if constexpr (TW_REGS) {
-        wa0 = __ldg(a.tab + (v - 1) + (1 << LN16)); wb0 = __ldg(a.tab + (v - 1) + (2 << LN16));
-        wc0 = __ldg(a.tab + (v - 1) + (4 << LN16)); wd0 = __ldg(a.tab + (v - 1) + (8 << LN16));
-    }
+    // w^8, w^4, w^2, w (h = 1, 2, 4, 8) are re-read per tile (L1 hits); h = 5, 9, 10, 11 are w^2 * W8, w * W16, w * W8,
+    // w * W16^3, rebuilt per tile (16 FP64 instructions). Keeping the four powers in registers for the whole kernel was worth
+    // 4 % at N = 4096 while tiles were assigned statically (1.31 vs 1.36 ms); with the tile hand-out below it spills (24 bytes)
+    // and loses: same box, N = 4096 x 65536, best of 60: registers 1.35-1.46 ms, re-read 1.27-1.29 ms (round-1 kernel 1.29-1.37).
+    // The smaller sizes never kept them: N = 512 1.41 -> 1.35, N = 1024 1.46 -> 1.33, N = 2048 1.42 -> 1.30 ms.
     const int rd1 = j * N + cp + 256 * kloc1;   // sub-pass 1 gather base
     const int wr1 = j * N + v;                  // sub-pass 1 scatter base
     const int rd2 = j * N + 16 * v;             // sub-pass 2 gather base
     const cd* const tw1p = tw1s + kloc1 * 8;
     const double sc = a.scale;
 
-    int b = g % PIPE_STAGES;   // ring slot of tile k
+    int b = g % PIPE_STAGES;   // buffer of ring slot k
     uint32_t round = 0;        // k / PIPE_STAGES
-    for (int k = g; k < my_tiles; k += 2) {
+    for (;;) {
         cd* const sm = bufs + (size_t)b * SLOT;
+        if (t == 0) next_of[g] = ahead;   // (parks the counter value read during the previous tile)
         mbar_wait_bounded(&full[b + PIPE_STAGES * (round & 1)], (round >> 1) & 1);
+        {
+            const int tile_k = tile_of[b + PIPE_STAGES * (round & 1)];
+            if (tile_k < 0) {   // the work is finished: tell the group waiting for the slot this one would have loaded
+                if (t == 0) issue(0x7fffffff, b, round + 1);
+                break;
+            }
+            if (t == 0) cur_of[PIPE_STAGES * g + b] = tile_k;   // read by the whole group after its next barrier; rewritten three tiles later
+        }
         cd x[16];
-        const long long tile_k = first + (long long)k * stride;
-        const int rows_left = (int)(a.batch - tile_k * NTR < NTR ? a.batch - tile_k * NTR : NTR);   // caller's transforms in this tile; a pair's
+        int rows_left = NTR;
+        if constexpr (REAL != PIPE_C2C) {
+            const long long tile_k = tile_of[b + PIPE_STAGES * (round & 1)];   // (still intact: the slot three ahead is not loaded before this group's last gather)
+            if (a.batch - tile_k * NTR < NTR) rows_left = (int)(a.batch - tile_k * NTR);
+        }
+        (void)rows_left;   // caller's transforms in this tile; a pair's
                                                                                                     // second row beyond them reads as zeros
         // ---- sub-pass 0: radix R0, exact constants, in place (each thread owns idx = t + 256 e) ----
 #pragma unroll
@@ -286,17 +326,12 @@ __global__ void __launch_bounds__(2 * PIPE_GROUP, 1) fft_pipe_kernel(const PipeA
         // ---- sub-pass 2: radix 16, M = N/16, S = 1 ----
 #pragma unroll
         for (int rho = 0; rho < 16; rho++) x[bitrev_c<4>(rho)] = sm[pipe_swz(rd2 + rho)];
-        cd wa, wb, wc, wd;
-        if constexpr (TW_REGS) {
-            wa = wa0; wb = wb0; wc = wc0; wd = wd0;
-        } else {
-            wa = __ldg(a.tab + (v - 1) + (1 << LN16)); wb = __ldg(a.tab + (v - 1) + (2 << LN16));
-            wc = __ldg(a.tab + (v - 1) + (4 << LN16)); wd = __ldg(a.tab + (v - 1) + (8 << LN16));
-        }
+        const cd wa = __ldg(a.tab + (v - 1) + (1 << LN16)), wb = __ldg(a.tab + (v - 1) + (2 << LN16));
+        const cd wc = __ldg(a.tab + (v - 1) + (4 << LN16)), wd = __ldg(a.tab + (v - 1) + (8 << LN16));
         group_sync(g);  // the buffer is free: refill it with this CTA's tile k + 3 (r2c: after the partner exchange below)
-        if (REAL != PIPE_R2C && t == 0 && k + PIPE_STAGES < my_tiles) {
+        if (REAL != PIPE_R2C && t == 0) {
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            issue(k + PIPE_STAGES, b, round + 1);
+            issue(next_of[g], b, round + 1);
         }
         {
             constexpr double C8 = 0.70710678118654752440, C16 = 0.92387953251128675613, S16 = 0.38268343236508977173;
@@ -309,7 +344,7 @@ __global__ void __launch_bounds__(2 * PIPE_GROUP, 1) fft_pipe_kernel(const PipeA
             SubStageSym<4, 1, 0, 0>::run(x, tw);
         }
         {
-            const long long tile = first + (long long)k * stride;
+            const long long tile = cur_of[PIPE_STAGES * g + b];   // (re-read: one register less to carry through the butterflies)
             const bool valid = tile * NT + j < a.batch;
             if constexpr (REAL == PIPE_R2C) {
                 // x[q] = Z[k], k = v + (q << LN16). The bins k < N/2 (q < 8) need the partner Z[N - k], held as q' = 15 - q by thread
@@ -324,9 +359,9 @@ __global__ void __launch_bounds__(2 * PIPE_GROUP, 1) fft_pipe_kernel(const PipeA
                     x[8 + q] = kk == 0 ? x[0] : sm[j * N + N - kk];
                 }
                 group_sync(g);  // now the buffer is free
-                if (t == 0 && k + PIPE_STAGES < my_tiles) {
+                if (t == 0) {
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                    issue(k + PIPE_STAGES, b, round + 1);
+                    issue(next_of[g], b, round + 1);
                 }
                 // X_a = (Z + conj W) / 2 -> row 2j, X_b = (Z - conj W) / 2i -> row 2j + 1; bins 0 .. N/2 - 1, and the Nyquist bins (v == 0)
                 const long long row = tile * NTR + 2 * j;
@@ -404,10 +439,14 @@ __global__ void __launch_bounds__(2 * PIPE_GROUP, 1) fft_pipe_kernel(const PipeA
                 }
             }
         }
+        if (t == 0) ahead = take();   // for the load this group issues while it works on its next tile
         // the other group consumed the next ring slot; this group's next tile is two slots ahead
         b += 2;
         if (b >= PIPE_STAGES) { b -= PIPE_STAGES; round++; }
     }
+    // every counter read of this CTA has returned (its value was parked or used): the last CTA resets the counters
+    __syncthreads();
+    if (threadIdx.x == 0 && atomicInc(a.sched + 1, gridDim.x - 1) == gridDim.x - 1) a.sched[0] = 0;
 }
 
 }  // namespace fftb200

@@ -26,6 +26,7 @@
 #include "fft_fused.cuh"
 #include "fft_pipe.cuh"
 #include "fft_pipe13.cuh"
+#include "fft_pipe13t.cuh"
 #include "fft_lastpipe.cuh"
 
 using namespace fftb200;
@@ -257,6 +258,7 @@ struct Pass {
     const KernelInfo* k;   // nullptr: persistent TMA kernel fft_pipe_kernel<log_p>, or the fused kernel when fused_lm > 0
     int fused_lm = 0, fused_lr = 0;   // fft_fused_kernel<fused_lm, fused_lr>: both passes in one launch
     int fused_cols = 0;               // column mode: stages 1 .. 16 of a larger transform, rows of 2^(log_n - 16) columns
+    int tmem13 = 0;                   // N = 8192: the tensor-memory variant (fft_pipe13t.cuh) instead of fft_pipe13.cuh
     int lastpipe = 0;                 // LAST tile pass with a TMA-ring twin (fft_lastpipe.cuh), used when nothing rides on the pass
     int log_p;
     int log_m;
@@ -286,6 +288,7 @@ struct fftb200_plan {
     cd* fscratch = nullptr;    // fused plans: L2-resident ring of `slots` groups of transforms
     size_t fscratch_elems = 0;
     int* fflags = nullptr;     // fused plans: per-group completion counters
+    unsigned int* sched = nullptr;   // persistent kernels: tile hand-out counters (zero between launches, the kernels reset them)
     size_t fflags_count = 0;
     cd fdtw[3][16];            // fused plans: pass-B derived-twiddle constants (fft_fused.cuh: fused_twiddles)
     cd* own_tab = nullptr;     // partial plans with a private (rank-specific) twiddle table
@@ -378,11 +381,13 @@ static int build_passes(fftb200_plan* p, DeviceState* ds) {
         ps.k = nullptr; ps.log_p = 13; ps.log_m = 0;
         ps.nt = 1; ps.shift = 0;
         ps.src = BUF_IN; ps.dst = BUF_OUT; ps.final_pass = 1;
+        ps.tmem13 = getenv("FFTB200_PIPE13_TMEM") ? 1 : 0;   // measured 1.82 vs 1.77 ms per 2^28 points: opt-in only
         for (int iv = 0; iv < 2; iv++)
-            CU(cudaFuncSetAttribute(pipe13_func(iv), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PIPE_SMEM));
+            CU(cudaFuncSetAttribute(ps.tmem13 ? pipe13t_func(iv) : pipe13_func(iv), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PIPE_SMEM));
         ps.grid_max = ds->sms;
         p->passes.push_back(ps);
-        p->desc += "P13(tma ring 3 x 64KB halves, 2x256 thr, de-interleave on the first gather, stage 13 traded through shared memory)";
+        p->desc += ps.tmem13 ? "P13t(tma ring 3 x 64KB halves, one 256-thread group per transform, radix-2 first, b and X[2k] parked in tensor memory)"
+                             : "P13(tma ring 3 x 64KB halves, 2x256 thr, de-interleave on the first gather, stage 13 traded through shared memory)";
         return 0;
     }
     if (L >= 13 && L <= 20 && p->acc && !getenv("FFTB200_NO_FUSED")) {
@@ -512,6 +517,18 @@ static EncodeTiledFn encode_tiled_fn() {
             cudaGetLastError();
     });
     return fn;
+}
+
+// Tile hand-out counters of the persistent kernels (fft_pipe.cuh "Tile order"): allocated and zeroed once, the kernels leave them at zero.
+// FFTB200_STATIC_TILES=1 keeps the fixed tile-to-CTA assignment (A/B measurements).
+static unsigned int* sched_counters(fftb200_plan* p) {
+    if (getenv("FFTB200_STATIC_TILES")) return nullptr;
+    if (!p->sched) {
+        p->sched = (unsigned int*)fftb200_malloc(sizeof(unsigned int) * 8);
+        if (!p->sched) { cudaGetLastError(); return nullptr; }
+        if (cudaMemset(p->sched, 0, sizeof(unsigned int) * 8) != cudaSuccess) { cudaFree(p->sched); p->sched = nullptr; cudaGetLastError(); return nullptr; }
+    }
+    return p->sched;
 }
 
 // Enqueue the fused two-pass kernel (fft_fused.cuh) for `nbatch` transforms.
@@ -732,8 +749,9 @@ static int enqueue_c2c(fftb200_plan* p, const cd* in, cd* out, int inverse, long
             pa.in = in; pa.out = out; pa.tab = p->acc;
             pa.ntiles = ntiles; pa.batch = nbatch;
             pa.inverse = inverse; pa.scale = p->scale;
+            pa.sched = sched_counters(p);
             if (ps.log_p == 13) {
-                CU(launch_pipe13(pa, grid, p->stream));
+                CU(ps.tmem13 ? launch_pipe13t(pa, grid, p->stream) : launch_pipe13(pa, grid, p->stream));
                 continue;
             }
             CU(launch_pipe(ps.log_p, pa, grid, p->stream));
@@ -1248,6 +1266,7 @@ static int exec_range(fftb200_plan* p, const void* d_in, void* d_out, long long 
         pa.in = (const cd*)d_in; pa.out = (cd*)d_out; pa.tab = p->acc;
         pa.ntiles = ntiles; pa.batch = nbatch;
         pa.inverse = p->kind == FFTB200_C2R; pa.scale = p->scale;
+        pa.sched = sched_counters(p);
         CU(launch_pipe_real(ps.log_p, p->kind == FFTB200_R2C ? PIPE_R2C : PIPE_C2R, pa, (int)(ntiles < ps.grid_max ? ntiles : ps.grid_max), p->stream));
         return 0;
     }
@@ -1293,6 +1312,7 @@ static int exec_range(fftb200_plan* p, const void* d_in, void* d_out, long long 
         const int grid = (int)(ntiles < ps.grid_max ? ntiles : ps.grid_max);
         PipeArgs pa;
         pa.tab = p->acc; pa.ntiles = ntiles; pa.batch = nbatch;
+        pa.sched = sched_counters(p);
         pa.chirp = p->chirp; pa.fb = p->fb; pa.n_user = p->n; pa.y_scale = inverse ? 1.0 / (double)p->n : 1.0;
         pa.in = (const cd*)d_in; pa.out = p->work; pa.inverse = 0; pa.scale = 1.0;
         CU(launch_pipe_real(ps.log_p, PIPE_BLUE_FWD, pa, grid, p->stream));
@@ -1442,6 +1462,7 @@ extern "C" void fftb200_plan_destroy(fftb200_plan* p) {
     if (p->scratch) cudaFree(p->scratch);
     if (p->fscratch) cudaFree(p->fscratch);
     if (p->fflags) cudaFree(p->fflags);
+    if (p->sched) cudaFree(p->sched);
     if (p->own_tab) cudaFree(p->own_tab);
     if (p->work) cudaFree(p->work);
     if (p->chirp) cudaFree(p->chirp);
