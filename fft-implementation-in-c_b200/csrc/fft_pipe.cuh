@@ -171,6 +171,8 @@ __global__ void __launch_bounds__(2 * PIPE_GROUP, 1) fft_pipe_kernel(const PipeA
     int* const next_of = tile_of + 2 * PIPE_STAGES;                        // [2]: the tile a group will load next
     int* const cur_of = next_of + 2;                                       // [2][3]: the tile a group works on (its own copy: tile_of[] is
                                                                            // rewritten as soon as the slot three ahead is loaded or closed)
+    int* const told_of = cur_of + 2 * PIPE_STAGES;                         // [2]: a slot of the OTHER group has been closed (by this group, or at start-up)
+    int* const leave_of = told_of + 2;                                     // [2]: thread 0's verdict for its group
 
     const int g = threadIdx.x / PIPE_GROUP, t = threadIdx.x % PIPE_GROUP;
     const int first = blockIdx.x, stride = gridDim.x;
@@ -178,11 +180,16 @@ __global__ void __launch_bounds__(2 * PIPE_GROUP, 1) fft_pipe_kernel(const PipeA
     // Tile order. The SMs of this chip do not move data at the same rate (a plain copy with a fixed tile-to-CTA assignment reaches
     // 6.0-6.4 TB/s, the same copy with tiles handed out on demand 6.9-7.0: tools/copybench.cu, profiles/r02_microbench.md), so a CTA
     // takes its first three tiles by position (CTA + k * grid: nothing to wait for at start-up) and every later one from a global
-    // counter: ring slot s of the CTA (buffer s % 3, group s % 2) carries whatever tile its loader was handed, the number travels in
-    // shared memory next to the barrier, and a number past the end (-1) tells the group that waits for the slot to stop - after it
-    // has passed the same message to the slot three ahead, whose loader it would have been. The counter is read one tile ahead
-    // (after a tile's results have left, when no butterfly registers are live) so that its latency stays off the critical path,
-    // and the last CTA to finish sets it back to zero for the next launch.
+    // counter: ring slot s of the CTA (buffer s % 3, group s % 2) carries whatever tile its loader was handed and the number travels in
+    // shared memory next to the barrier. The counter is read one tile ahead (after a tile's results have left, when no butterfly
+    // registers are live) so that its latency stays off the critical path, and the last CTA to finish sets it back to zero for the
+    // next launch.
+    // End of work. A number past the end closes a slot (-1, the barrier's phase completed without data). Each group reads the counter
+    // in the order of the slots it loads, and once the counter has run out it stays so; hence (a) after the first closed slot a group
+    // finds, every later slot of its own is closed too: nothing left to compute; (b) but the number it holds for the other group's
+    // next slot may have been read earlier and still be a tile. So a group keeps walking its slots - passing on what it holds, reading
+    // the counter again - until it has both FOUND a closed slot and CLOSED one itself: then the other group is sure to find a closed
+    // slot, and no tile that was handed out is left unloaded. (At most two empty turns per group.)
     // (tile numbers fit 32 bits: 2^31 tiles of 64 KB are more than any memory holds; clamped so that they never wrap)
     auto take = [&]() -> int {   // the tile of this group's next load
         const unsigned v = 3u * gridDim.x + atomicAdd(a.sched, 1u);
@@ -195,12 +202,12 @@ __global__ void __launch_bounds__(2 * PIPE_GROUP, 1) fft_pipe_kernel(const PipeA
     // parity wait then passes on the phase before: stale data, a second expect_tx in the same phase and a launch failure;
     // seen on the B200 about once per 10^7 tiles). So each buffer has TWO barriers used in turn (bar = b + 3 * (round & 1),
     // parity (round >> 1) & 1): all phases of one barrier are waited for by the same group, in program order.
-    auto issue = [&](int tile, int b, uint32_t rnd) {  // one thread: start the load of `tile` into buffer b
+    auto issue = [&](int tile, int b, uint32_t rnd) -> bool {  // one thread: start the load of `tile` into buffer b; true = nothing left, slot closed
         uint64_t* const bar = &full[b + PIPE_STAGES * (rnd & 1)];
         if (tile >= a.ntiles) {   // nothing left: complete the phase without data
             tile_of[b + PIPE_STAGES * (rnd & 1)] = -1;
             mbar_arrive(bar);
-            return;
+            return true;
         }
         tile_of[b + PIPE_STAGES * (rnd & 1)] = tile;
         long long nvalid = a.batch - (long long)tile * NTR;
@@ -210,6 +217,7 @@ __global__ void __launch_bounds__(2 * PIPE_GROUP, 1) fft_pipe_kernel(const PipeA
         const uint32_t bytes = (uint32_t)nvalid * per;
         mbar_expect_tx(bar, bytes);
         bulk_load(bufs + (size_t)b * SLOT, reinterpret_cast<const char*>(a.in) + (size_t)tile * NTR * per, bytes, bar);
+        return false;
     };
 
     if (threadIdx.x == 0) {
@@ -227,8 +235,11 @@ __global__ void __launch_bounds__(2 * PIPE_GROUP, 1) fft_pipe_kernel(const PipeA
     }
     __syncthreads();
     if (threadIdx.x == 0) {
-        for (int k = 0; k < PIPE_STAGES; k++) issue((long long)first + (long long)k * stride < a.ntiles ? first + k * stride : 0x7fffffff, k, 0);
+        told_of[0] = told_of[1] = 0;
+        for (int k = 0; k < PIPE_STAGES; k++)   // (slot k belongs to group k % 2: closed here counts as closed by the other one)
+            if (issue((long long)first + (long long)k * stride < a.ntiles ? first + k * stride : 0x7fffffff, k, 0)) told_of[(k + 1) & 1] = 1;
     }
+    __syncthreads();
     int ahead = 0;   // thread 0 of a group: the tile its next load will fetch
     if (t == 0) ahead = take();
 
@@ -256,9 +267,19 @@ __global__ void __launch_bounds__(2 * PIPE_GROUP, 1) fft_pipe_kernel(const PipeA
         mbar_wait_bounded(&full[b + PIPE_STAGES * (round & 1)], (round >> 1) & 1);
         {
             const int tile_k = tile_of[b + PIPE_STAGES * (round & 1)];
-            if (tile_k < 0) {   // the work is finished: tell the group waiting for the slot this one would have loaded
-                if (t == 0) issue(0x7fffffff, b, round + 1);
-                break;
+            if (tile_k < 0) {   // a closed slot: pass on what this group holds for the slot three ahead; leave once the other group is sure to find a closed slot
+                if (t == 0) {
+                    if (issue(next_of[g], b, round + 1)) told_of[g] = 1;
+                    leave_of[g] = told_of[g];
+                }
+                group_sync(g);
+                const int leave = leave_of[g];
+                group_sync(g);
+                if (leave) break;
+                if (t == 0) ahead = take();
+                b += 2;
+                if (b >= PIPE_STAGES) { b -= PIPE_STAGES; round++; }
+                continue;
             }
             if (t == 0) cur_of[PIPE_STAGES * g + b] = tile_k;   // read by the whole group after its next barrier; rewritten three tiles later
         }
@@ -331,7 +352,7 @@ __global__ void __launch_bounds__(2 * PIPE_GROUP, 1) fft_pipe_kernel(const PipeA
         group_sync(g);  // the buffer is free: refill it with this CTA's tile k + 3 (r2c: after the partner exchange below)
         if (REAL != PIPE_R2C && t == 0) {
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            issue(next_of[g], b, round + 1);
+            if (issue(next_of[g], b, round + 1)) told_of[g] = 1;
         }
         {
             constexpr double C8 = 0.70710678118654752440, C16 = 0.92387953251128675613, S16 = 0.38268343236508977173;
@@ -361,7 +382,7 @@ __global__ void __launch_bounds__(2 * PIPE_GROUP, 1) fft_pipe_kernel(const PipeA
                 group_sync(g);  // now the buffer is free
                 if (t == 0) {
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                    issue(next_of[g], b, round + 1);
+                    if (issue(next_of[g], b, round + 1)) told_of[g] = 1;
                 }
                 // X_a = (Z + conj W) / 2 -> row 2j, X_b = (Z - conj W) / 2i -> row 2j + 1; bins 0 .. N/2 - 1, and the Nyquist bins (v == 0)
                 const long long row = tile * NTR + 2 * j;

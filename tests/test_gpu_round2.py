@@ -413,3 +413,36 @@ def test_real_transforms_are_bit_stable_over_many_executions(gpu, port, kind, n,
         assert L.fftb200_plan_exec(plan, src.data_ptr(), dst.data_ptr()) == 0, L.fftb200_last_error()
         assert torch.equal(torch.view_as_real(dst) if kind == "r2c" else dst, torch.view_as_real(first) if kind == "r2c" else first), it
     L.fftb200_plan_destroy(plan)
+
+
+@pytest.mark.parametrize("n", [512, 1024, 4096])
+def test_tile_hand_out_covers_every_tile_once(gpu, n):
+    """fft_pipe_kernel takes its first three tiles per CTA by position and the rest from a global counter that the last CTA resets
+    (csrc/fft_pipe.cuh "Tile order"). Batches around the multiples of the grid (1 .. 3 x 148 tiles and beyond, ragged last tiles), both
+    directions, several executions of the same plan in a row: every row against numpy, and the same bits every time - a tile handed out
+    twice, never, or after a counter that was not reset shows up as a wrong or a stale row."""
+    import torch
+    L = gpu.lib
+    nt = 4096 // n
+    sms = torch.cuda.get_device_properties(0).multi_processor_count
+    rng = np.random.default_rng(5)
+    batches = [1, nt + 1, 2 * nt, sms * nt - 1, sms * nt, sms * nt + 1, 3 * sms * nt - 1, 3 * sms * nt, 3 * sms * nt + 1, 4 * sms * nt + 3, 11 * sms * nt + 5]
+    for batch in batches:
+        x = (rng.standard_normal((batch, n)) + 1j * rng.standard_normal((batch, n)))
+        src = torch.from_numpy(x).cuda()
+        dst = torch.empty_like(src)
+        for direction in (-1, 1):
+            plan = gpu.engine_plan(n, batch, gpu.FFTB200_C2C, direction)
+            want = np.fft.fft(x, axis=1) if direction < 0 else np.fft.ifft(x, axis=1)
+            first = None
+            for it in range(4):
+                dst.fill_(float("nan"))
+                assert L.fftb200_plan_exec(plan, src.data_ptr(), dst.data_ptr()) == 0, L.fftb200_last_error()
+                got = dst.cpu().numpy()
+                if first is None:
+                    first = got
+                    err = np.linalg.norm(got - want, axis=1) / np.linalg.norm(want, axis=1)
+                    assert np.all(err <= TOL), (n, batch, direction, int(np.argmax(err)), float(err.max()))
+                else:
+                    assert np.array_equal(got, first), (n, batch, direction, it)
+            L.fftb200_plan_destroy(plan)
