@@ -27,6 +27,7 @@ struct LastPipeArgs {
     int log_n, log_m;   // N = 2^log_n, M = 2^log_m stages-worth of points done by earlier passes
     int inverse;
     double scale;       // applied with the final conjugation when inverse
+    unsigned int* sched;   // tile hand-out counters (fft_pipe.cuh "Tile order"): [0] tiles taken beyond the first three per CTA, [1] CTAs finished
 };
 
 template <int R>
@@ -49,17 +50,32 @@ __global__ void __launch_bounds__(2 * PIPE_GROUP, 1) fft_lastpipe_kernel(const L
 
     const int g2 = threadIdx.x / PIPE_GROUP, t = threadIdx.x % PIPE_GROUP;
     const int first = blockIdx.x, stride = gridDim.x;
-    const int my_tiles = first < a.ntiles ? (int)((a.ntiles - first + stride - 1) / stride) : 0;
     const int lm = a.log_m;
     const double sc = a.scale;
+    // tiles handed out on demand, exactly as in fft_pipe_kernel ("Tile order" / "End of work" there): the first three of a CTA by
+    // position, the others from the global counter in the same batch-first order, read one tile ahead
+    int* const tile_of = reinterpret_cast<int*>(full + 2 * PIPE_STAGES);   // [6]: the tile of a barrier's current phase, -1 = closed
+    int* const next_of = tile_of + 2 * PIPE_STAGES;                        // [2]: the tile a group will load next
+    int* const told_of = next_of + 2;                                      // [2]: a slot of the other group has been closed
+    int* const leave_of = told_of + 2;                                     // [2]
+    auto take = [&]() -> int {
+        const unsigned v = 3u * gridDim.x + atomicAdd(a.sched, 1u);
+        return v < 0x7fffffffu ? (int)v : 0x7fffffff;
+    };
 
     // same two-barriers-per-buffer scheme as fft_pipe_kernel
-    auto issue = [&](int k, int b, uint32_t rnd) {
-        const long long tile = first + (long long)k * stride;
-        const long long tr = tile % a.batch, kb = tile / a.batch;
+    auto issue = [&](int tile, int b, uint32_t rnd) -> bool {   // true: nothing left, the slot is closed
         uint64_t* const bar = &full[b + PIPE_STAGES * (rnd & 1)];
+        if (tile >= a.ntiles) {
+            tile_of[b + PIPE_STAGES * (rnd & 1)] = -1;
+            mbar_arrive(bar);
+            return true;
+        }
+        tile_of[b + PIPE_STAGES * (rnd & 1)] = tile;
+        const long long tr = tile % a.batch, kb = tile / a.batch;
         mbar_expect_tx(bar, PIPE_TILE * (uint32_t)sizeof(cd));
         bulk_load(bufs + (size_t)b * PIPE_TILE, a.in + (tr << a.log_n) + (kb << 12), PIPE_TILE * (uint32_t)sizeof(cd), bar);
+        return false;
     };
     if (threadIdx.x == 0) {
 #pragma unroll
@@ -69,20 +85,40 @@ __global__ void __launch_bounds__(2 * PIPE_GROUP, 1) fft_lastpipe_kernel(const L
     }
     __syncthreads();
     if (threadIdx.x == 0) {
-        for (int k = 0; k < PIPE_STAGES && k < my_tiles; k++) issue(k, k, 0);
+        told_of[0] = told_of[1] = 0;
+        for (int k = 0; k < PIPE_STAGES; k++)
+            if (issue((long long)first + (long long)k * stride < a.ntiles ? first + k * stride : 0x7fffffff, k, 0)) told_of[(k + 1) & 1] = 1;
     }
+    __syncthreads();
+    int ahead = 0;
+    if (t == 0) ahead = take();
 
     typedef typename SwzBlast<LR>::type SWL;
     typedef typename std::conditional<B3, SwzId, SWL>::type SW1;   // layout after sub-pass 0
 
     int b = g2 % PIPE_STAGES;
     uint32_t round = 0;
-    for (int k = g2; k < my_tiles; k += 2) {
+    for (;;) {
         cd* const sm = bufs + (size_t)b * PIPE_TILE;
-        const long long tile = first + (long long)k * stride;
+        if (t == 0) next_of[g2] = ahead;
+        mbar_wait_bounded(&full[b + PIPE_STAGES * (round & 1)], (round >> 1) & 1);
+        const int tile = tile_of[b + PIPE_STAGES * (round & 1)];
+        if (tile < 0) {   // a closed slot: pass on what this group holds; leave once it has closed a slot of the other group as well
+            if (t == 0) {
+                if (issue(next_of[g2], b, round + 1)) told_of[g2] = 1;
+                leave_of[g2] = told_of[g2];
+            }
+            group_sync(g2);
+            const int leave = leave_of[g2];
+            group_sync(g2);
+            if (leave) break;
+            if (t == 0) ahead = take();
+            b += 2;
+            if (b >= PIPE_STAGES) { b -= PIPE_STAGES; round++; }
+            continue;
+        }
         const long long tr = tile % a.batch;
         const int kb = (int)(tile / a.batch);
-        mbar_wait_bounded(&full[b + PIPE_STAGES * (round & 1)], (round >> 1) & 1);
         cd x[16];
         {
             typedef Geo<0, LR, LC2, 0, RB0, false> G0;
@@ -124,9 +160,9 @@ __global__ void __launch_bounds__(2 * PIPE_GROUP, 1) fft_lastpipe_kernel(const L
         const GL gl(t);
         fused_gather<GL, SWL, 4, false>(x, sm, gl);
         group_sync(g2);   // the buffer is free: refill it with this CTA's tile k + 3
-        if (t == 0 && k + PIPE_STAGES < my_tiles) {
+        if (t == 0) {
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            issue(k + PIPE_STAGES, b, round + 1);
+            if (issue(next_of[g2], b, round + 1)) told_of[g2] = 1;
         }
         {
             // (asking for these 15 entries before the exchange settles - they only depend on the tile and the thread - spills
@@ -146,12 +182,15 @@ __global__ void __launch_bounds__(2 * PIPE_GROUP, 1) fft_lastpipe_kernel(const L
                 p[(size_t)q << (AL + lm)] = r;
             }
         }
+        if (t == 0) ahead = take();
         b += 2;
         if (b >= PIPE_STAGES) { b -= PIPE_STAGES; round++; }
     }
+    __syncthreads();   // every counter read of this CTA has returned: the last CTA to finish resets the counters
+    if (threadIdx.x == 0 && atomicInc(a.sched + 1, gridDim.x - 1) == gridDim.x - 1) a.sched[0] = 0;
 }
 
-constexpr size_t LASTPIPE_SMEM = (size_t)PIPE_STAGES * PIPE_TILE * sizeof(cd) + 64;
+constexpr size_t LASTPIPE_SMEM = (size_t)PIPE_STAGES * PIPE_TILE * sizeof(cd) + 128;   // + barriers, tile numbers
 const void* lastpipe_func(int lr, int inverse);   // fft_kernels_lastpipe.cu
 cudaError_t launch_lastpipe(int lr, const LastPipeArgs& a, int grid, cudaStream_t s);
 

@@ -67,14 +67,25 @@ __global__ void __launch_bounds__(2 * PIPE_GROUP, 1) fft_pipe13_kernel(const Pip
     cd* const tw1s = bufs + (size_t)PIPE_STAGES * PIPE_TILE;
     uint64_t* const full = reinterpret_cast<uint64_t*>(tw1s + PIPE_TW1);
 
+    int* const tr_of = reinterpret_cast<int*>(full + 2 * PIPE_STAGES);   // [4]: the transform behind this CTA's k-th turn, k & 3
+
     const int g = threadIdx.x / PIPE_GROUP, t = threadIdx.x % PIPE_GROUP;
     const int first = blockIdx.x, stride = gridDim.x;
-    const int my_tr = first < a.ntiles ? (int)((a.ntiles - first + stride - 1) / stride) : 0;   // transforms of this CTA
-    const int my_halves = 2 * my_tr;
+
+    // Transforms are handed out on demand (fft_pipe.cuh "Tile order": the SMs do not all move data at the same rate). The two groups
+    // of this kernel work on the same transform in lock step, so one thread keeps the list: the first two transforms of a CTA by
+    // position, every later one from the global counter, read at the end of turn k - 1 for turn k + 2, parked in shared memory at the
+    // top of turn k (in front of that turn's CTA-wide barriers) and used from turn k's refills on. A number past the end (the counter
+    // stays exhausted once it is) ends the CTA at the turn that would have worked on it; halves of such a transform are never loaded.
+    auto take = [&]() -> int {
+        const unsigned v = 2u * gridDim.x + atomicAdd(a.sched, 1u);
+        return v < 0x7fffffffu ? (int)v : 0x7fffffff;
+    };
 
     // half h = 2 k + (h & 1) of this CTA's k-th transform = elements [4096 (h & 1), + 4096) -> buffer b (= h % 3)
     auto issue = [&](int h, int b, uint32_t rnd) {
-        const long long tr = first + (long long)(h >> 1) * stride;
+        const long long tr = tr_of[(h >> 1) & 3];
+        if (tr >= a.ntiles) return;
         uint64_t* const bar = &full[b + PIPE_STAGES * (rnd & 1)];
         mbar_expect_tx(bar, H * (uint32_t)sizeof(cd));
         bulk_load(bufs + (size_t)b * PIPE_TILE, a.in + tr * N + (h & 1) * H, H * (uint32_t)sizeof(cd), bar);
@@ -91,9 +102,15 @@ __global__ void __launch_bounds__(2 * PIPE_GROUP, 1) fft_pipe13_kernel(const Pip
         const int kl = threadIdx.x >> 3, e = threadIdx.x & 7;
         tw1s[threadIdx.x] = __ldg(a.tab + ((sym_h(e) << 4) + kl - 1));
     }
+    int ahead = 0;   // thread 0: the transform of turn k + 2, until it is parked
+    if (threadIdx.x == 0) {
+        tr_of[0] = first < a.ntiles ? first : 0x7fffffff;
+        tr_of[1] = (long long)first + stride < a.ntiles ? first + stride : 0x7fffffff;
+        ahead = take();
+    }
     __syncthreads();
     if (threadIdx.x == 0) {
-        for (int h = 0; h < PIPE_STAGES && h < my_halves; h++) issue(h, h, 0);
+        for (int h = 0; h < PIPE_STAGES; h++) issue(h, h, 0);
     }
 
     const int cp = t & 15, kloc1 = t >> 4;
@@ -103,8 +120,10 @@ __global__ void __launch_bounds__(2 * PIPE_GROUP, 1) fft_pipe13_kernel(const Pip
 
     int b = g;                 // ring slot of half h (h % 3)
     uint32_t round = 0;        // h / 3
-    for (int h = g; h < my_halves; h += 2) {
+    for (int h = g;; h += 2) {
         cd* const sm = bufs + (size_t)b * PIPE_TILE;
+        if (threadIdx.x == 0) tr_of[((h >> 1) + 2) & 3] = ahead;
+        if (tr_of[(h >> 1) & 3] >= a.ntiles) break;   // (written two turns ago, or before the kernel's first barrier)
         mbar_wait_bounded(&full[b + PIPE_STAGES * (round & 1)], (round >> 1) & 1);   // a lost load traps instead of hanging the GPU
         cd x[16];
         // ---- sub-pass 0: radix 16, exact constants, in place ----
@@ -155,7 +174,7 @@ __global__ void __launch_bounds__(2 * PIPE_GROUP, 1) fft_pipe13_kernel(const Pip
         // group 0's buffer is free now: refill it with half h + 3 (the odd half of the next transform). Group 1's buffer
         // hosts the stage-13 trade first: tell group 0 that every gather from it is done.
         if (g == 0) {
-            if (t == 0 && h + PIPE_STAGES < my_halves) {
+            if (t == 0) {
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 issue(h + PIPE_STAGES, b, round + 1);
             }
@@ -194,21 +213,24 @@ __global__ void __launch_bounds__(2 * PIPE_GROUP, 1) fft_pipe13_kernel(const Pip
 #pragma unroll
             for (int e = 0; e < 8; e++) z[e] = xb[(g == 0 ? 2048 : 0) + 256 * e + t];
             bar_sync_n(5, 2 * PIPE_GROUP);       // the trade has been read: group 1's buffer is free
-            if (g == 1 && t == 0 && h + PIPE_STAGES < my_halves) {
+            if (g == 1 && t == 0) {
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 issue(h + PIPE_STAGES, b, round + 1);
             }
         }
         {
-            const long long tr = first + (long long)(h >> 1) * stride;
+            const long long tr = tr_of[(h >> 1) & 3];
             cd* const p = a.out + tr * N + t + (g ? 2048 : 0);
             const cd w13 = __ldg(a.tab + (H - 1) + t);   // stage 13, position t (L1-resident: the same entry for every transform)
             if (g == 0) Stage13<INV, false, 0>::run(x, z, w13, p, sc);
             else Stage13<INV, true, 0>::run(x + 8, z, w13, p, sc);
         }
+        if (threadIdx.x == 0) ahead = take();
         b += 2;
         if (b >= PIPE_STAGES) { b -= PIPE_STAGES; round++; }
     }
+    __syncthreads();   // every counter read of this CTA has returned: the last CTA to finish resets the counters
+    if (threadIdx.x == 0 && atomicInc(a.sched + 1, gridDim.x - 1) == gridDim.x - 1) a.sched[0] = 0;
 }
 
 const void* pipe13_func(int inverse);

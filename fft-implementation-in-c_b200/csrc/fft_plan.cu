@@ -520,13 +520,16 @@ static EncodeTiledFn encode_tiled_fn() {
 }
 
 // Tile hand-out counters of the persistent kernels (fft_pipe.cuh "Tile order"): allocated and zeroed once, the kernels leave them at zero.
-// FFTB200_STATIC_TILES=1 keeps the fixed tile-to-CTA assignment (A/B measurements).
+// One set per plan: the kernels of a plan run one after the other on the plan's stream.
 static unsigned int* sched_counters(fftb200_plan* p) {
-    if (getenv("FFTB200_STATIC_TILES")) return nullptr;
     if (!p->sched) {
         p->sched = (unsigned int*)fftb200_malloc(sizeof(unsigned int) * 8);
-        if (!p->sched) { cudaGetLastError(); return nullptr; }
-        if (cudaMemset(p->sched, 0, sizeof(unsigned int) * 8) != cudaSuccess) { cudaFree(p->sched); p->sched = nullptr; cudaGetLastError(); return nullptr; }
+        if (!p->sched) return nullptr;   // (fftb200_malloc has recorded the error)
+        if (cudaMemset(p->sched, 0, sizeof(unsigned int) * 8) != cudaSuccess) {
+            cudaFree(p->sched); p->sched = nullptr; cudaGetLastError();
+            fail("cudaMemset failed for the tile counters");
+            return nullptr;
+        }
     }
     return p->sched;
 }
@@ -750,6 +753,7 @@ static int enqueue_c2c(fftb200_plan* p, const cd* in, cd* out, int inverse, long
             pa.ntiles = ntiles; pa.batch = nbatch;
             pa.inverse = inverse; pa.scale = p->scale;
             pa.sched = sched_counters(p);
+            if (!pa.sched) return -1;
             if (ps.log_p == 13) {
                 CU(ps.tmem13 ? launch_pipe13t(pa, grid, p->stream) : launch_pipe13(pa, grid, p->stream));
                 continue;
@@ -767,6 +771,8 @@ static int enqueue_c2c(fftb200_plan* p, const cd* in, cd* out, int inverse, long
             la.batch = nbatch; la.log_n = p->log_n; la.log_m = ps.log_m;
             la.ntiles = nbatch << (ps.log_m - (12 - ps.log_p));
             la.inverse = inverse; la.scale = p->scale;
+            la.sched = sched_counters(p);
+            if (!la.sched) return -1;
             CU(launch_lastpipe(ps.log_p, la, (int)(la.ntiles < ps.lastpipe ? la.ntiles : ps.lastpipe), p->stream));
             continue;
         }
@@ -1267,6 +1273,7 @@ static int exec_range(fftb200_plan* p, const void* d_in, void* d_out, long long 
         pa.ntiles = ntiles; pa.batch = nbatch;
         pa.inverse = p->kind == FFTB200_C2R; pa.scale = p->scale;
         pa.sched = sched_counters(p);
+        if (!pa.sched) return -1;
         CU(launch_pipe_real(ps.log_p, p->kind == FFTB200_R2C ? PIPE_R2C : PIPE_C2R, pa, (int)(ntiles < ps.grid_max ? ntiles : ps.grid_max), p->stream));
         return 0;
     }
@@ -1313,6 +1320,7 @@ static int exec_range(fftb200_plan* p, const void* d_in, void* d_out, long long 
         PipeArgs pa;
         pa.tab = p->acc; pa.ntiles = ntiles; pa.batch = nbatch;
         pa.sched = sched_counters(p);
+        if (!pa.sched) return -1;
         pa.chirp = p->chirp; pa.fb = p->fb; pa.n_user = p->n; pa.y_scale = inverse ? 1.0 / (double)p->n : 1.0;
         pa.in = (const cd*)d_in; pa.out = p->work; pa.inverse = 0; pa.scale = 1.0;
         CU(launch_pipe_real(ps.log_p, PIPE_BLUE_FWD, pa, grid, p->stream));
