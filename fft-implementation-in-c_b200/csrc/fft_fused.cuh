@@ -83,6 +83,13 @@ struct FusedArgs {
     int log_cb;         // column mode: log2 of the 16-column blocks per transform (row length / 16)
     int debug;          // development only: 1 = pass A alone, 2 = pass B alone, 4 = ignore the dependency counters
     double scale;       // 1/N for the inverse
+    // Bluestein variants (BLUE): chirp of the caller's length n_user, spectrum FB of the wrapped chirp (N entries), the caller's arrays
+    const cd* chirp;
+    const cd* fb;
+    const cd* user_in;  // BLUE_FWD: n_user elements per transform (the partial last row of a transform is read from here)
+    cd* user_out;       // BLUE_INV: n_user elements per transform
+    int n_user;
+    double y_scale;     // 1/n_user for the inverse direction of the caller's transform, else 1
     cd dtw[3][16];      // pass B, sub-pass j: dtw[j][h] = T[stage][q << a_tot] (table entry at kappa = 0), h = 2^(s-1) + q
 };
 
@@ -384,7 +391,15 @@ __device__ __forceinline__ void fused_publish(int* counter) {
 // boxes: the tile's columns and the mirrored columns) and the first gather of pass A - no c2r_expand pass, no full-length work array.
 // C2R (inverse only): the input is the Hermitian-extended spectrum (c2r_expand_kernel), only the real parts of the result are
 // staged and stored (n doubles per transform, fft_auto.h:99-107): the separate real-part pass and its 24 bytes per point go away.
-template <int LM, int LR, bool INV, bool COLS = false, bool R2C = false, bool C2R = false, bool HERM = false>
+// BLUE = FUSED_BLUE_FWD / FUSED_BLUE_INV: the two transforms of Bluestein's algorithm (bluestein.c:107-148) for padded lengths
+// N = 2^14 .. 2^20 with the elementwise steps riding on them, as in fft_pipe_kernel for N <= 4096. FWD: pass A reads the caller's rows
+// of n_user elements through a 3-D tensor map whose rows end at the last full row of R elements (the rows behind it arrive as zeros:
+// the padding; the partial row is read from the caller's array in the first gather), multiplies by conj(chirp) in the first gather, and
+// pass B multiplies the spectrum by FB before it is staged. INV (inverse transform, 1/N): pass B multiplies by conj(chirp) * y_scale and
+// stores the first n_user values of every row from registers to the caller's array. Two launches and HBM round trips instead of five,
+// the same arithmetic as bluestein_pre / pointwise_mul / bluestein_post (fft_aux.cuh).
+enum { FUSED_BLUE_NONE = 0, FUSED_BLUE_FWD = 1, FUSED_BLUE_INV = 2 };
+template <int LM, int LR, bool INV, bool COLS = false, bool R2C = false, bool C2R = false, bool HERM = false, int BLUE = FUSED_BLUE_NONE>
 __global__ void __launch_bounds__(FUSED_THREADS, 1)
 fft_fused_kernel(const FusedArgs a, const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUtensorMap tm_sc,
                  const __grid_constant__ CUtensorMap tm_out, const __grid_constant__ CUtensorMap tm_out2) {
@@ -393,6 +408,7 @@ fft_fused_kernel(const FusedArgs a, const __grid_constant__ CUtensorMap tm_in, c
     static_assert(!R2C || (!INV && !COLS), "r2c is a forward transform of whole arrays");
     static_assert(!C2R || (INV && !COLS && !R2C), "c2r is an inverse transform of whole arrays");
     static_assert(!HERM || R2C || C2R, "the Hermitian variants belong to the real transforms");
+    static_assert(BLUE == FUSED_BLUE_NONE || (!COLS && !R2C && !C2R && INV == (BLUE == FUSED_BLUE_INV)), "Bluestein: forward transform first, inverse second");
     constexpr int LOGN = COLS ? 20 : LM + LR;             // points per (virtual) transform
     constexpr int LOG_TPT = LOGN - 12;
     // HERM: r2c with a Hermitian-aware schedule: the pass-A outputs of a real column satisfy Y_c[M - k] = conj(Y_c[k]), so only the
@@ -431,7 +447,7 @@ fft_fused_kernel(const FusedArgs a, const __grid_constant__ CUtensorMap tm_in, c
     // the store drain into the compute group's time. Same-box A/B at 2^28 points (ms, direct vs staged): 2^13 2.61 / 2.24,
     // 2^14 2.34 / 2.62, 2^15 2.34 / 2.59, 2^16 2.35 / 2.26, 2^17 2.55 / 2.50, 2^18 3.04 / 2.77, 2^19 3.00 / 2.79,
     // 2^20 3.39 / 2.95: it pays only for LR = 7 (rows of 32 elements, two sub-passes), which is where it is used.
-    constexpr bool BDIRECT = FUSED_BDIRECT && !COLS && !R2C && !C2R && LR == 7;
+    constexpr bool BDIRECT = (FUSED_BDIRECT && !COLS && !R2C && !C2R && LR == 7) || BLUE == FUSED_BLUE_INV;   // (the caller's rows of n_user elements cannot be a tensor box)
 
     extern __shared__ __align__(128) unsigned char smem_raw[];
     cd* const bufs = reinterpret_cast<cd*>(smem_raw);
@@ -503,7 +519,10 @@ fft_fused_kernel(const FusedArgs a, const __grid_constant__ CUtensorMap tm_in, c
 #pragma unroll
                 for (int q = 0; q < 4; q++) {
                     waitq(q);
-                    if constexpr (CH) {
+                    if constexpr (BLUE == FUSED_BLUE_FWD) {
+                        // the caller's rows: [transform][t < n_user / R][R]; rows from n_user / R on are out of range and arrive as zeros
+                        tma_load_3d(buf + q * QT, &tm_in, 2 * (blk << LC), q * (QT >> LC), (int)tr, &full[w], pol_first);
+                    } else if constexpr (CH) {
                         // the input is the HALF spectrum (N/2 + 1 bins per transform, rows of R): quarters 0, 1 = rows t < M/2 of the tile's columns;
                         // quarters 2, 3 = the same rows of the mirrored columns R - c0 - C + 1 .. R - c0 - the rows t >= M/2 of the Hermitian
                         // extension read backwards, X[c + R t] = conj(H[(R - c) + R (M - 1 - t)]) (column R of the first tile is out of range: zeros)
@@ -706,6 +725,28 @@ fft_fused_kernel(const FusedArgs a, const __grid_constant__ CUtensorMap tm_in, c
                         SubStageExact<RA0, 1, 0, 0>::run(&x[bb * R0]);
                         fused_scatter<G0, SwzId, RA0>(&x[bb * R0], sm, G0(t + PIPE_GROUP * bb));
                     }
+                } else if constexpr (BLUE == FUSED_BLUE_FWD) {
+                    // a = x * conj(chirp), zero-padded from n_user to N (bluestein.c:107-109): element (t, c) of the tile is x[c + R t]
+                    const cd* const urow = a.user_in + ((size_t)kg * a.gt + ktr) * (size_t)a.n_user;
+                    const int t_full = a.n_user >> LR;   // rows the tensor map holds; row t_full is the partial one
+#pragma unroll
+                    for (int bb = 0; bb < NB; bb++) {
+                        const G0 g(t + PIPE_GROUP * bb);
+                        const int base = g.gbase();
+#pragma unroll
+                        for (int rho = 0; rho < R0; rho++) {
+                            const int I = base + rho * G0::GSTRIDE, tt = I >> LC;
+                            const int i = (kb << LC) + (I & ((1 << LC) - 1)) + (tt << LR);
+                            cd y = make_double2(0.0, 0.0);
+                            if (i < a.n_user) {
+                                const cd xv = tt == t_full ? __ldg(urow + i) : sm[I], w = __ldg(a.chirp + i);
+                                y = make_double2(fma(xv.x, w.x, xv.y * w.y), fma(xv.y, w.x, -(xv.x * w.y)));
+                            }
+                            x[bb * R0 + bitrev_c<RA0>(rho)] = y;
+                        }
+                        SubStageExact<RA0, 1, 0, 0>::run(&x[bb * R0]);
+                        fused_scatter<G0, SwzId, RA0>(&x[bb * R0], sm, g);
+                    }
                 } else {
 #pragma unroll
                     for (int bb = 0; bb < NB; bb++) {
@@ -883,12 +924,38 @@ fft_fused_kernel(const FusedArgs a, const __grid_constant__ CUtensorMap tm_in, c
                 // X[k + M q], k = (kb << LC2) + hi, q = kloc + (q' << AL): lanes run over hi first, so a warp instruction writes
                 // 32 / C2 rows of C2 contiguous elements (>= 64 bytes each)
                 const long long tr = (long long)kg * a.gt + ktr;
-                cd* p = a.out + ((size_t)tr << LOGN) + ((size_t)kb << LC2) + gl.hi + ((size_t)gl.kloc << LM);
+                if constexpr (BLUE == FUSED_BLUE_INV) {
+                    // y = a * conj(chirp) * y_scale for the first n_user values of the row (bluestein.c:139-148), factors fetched four at a time
+                    const int j0 = (kb << LC2) + gl.hi + (gl.kloc << LM);
+                    cd* const p = a.user_out + (size_t)tr * (size_t)a.n_user + j0;
+                    const double s2 = a.y_scale;
 #pragma unroll
-                for (int q = 0; q < 16; q++) {
-                    cd r = x[q];
-                    if (INV) { r.x *= sc; r.y *= -sc; }
-                    p[(size_t)q << (AL + LM)] = r;
+                    for (int q0 = 0; q0 < 16; q0 += 4) {
+                        cd w[4];
+#pragma unroll
+                        for (int i = 0; i < 4; i++) {
+                            const int j = j0 + ((q0 + i) << (AL + LM));
+                            w[i] = j < a.n_user ? __ldg(a.chirp + j) : make_double2(0.0, 0.0);
+                        }
+#pragma unroll
+                        for (int i = 0; i < 4; i++) {
+                            cd r = x[q0 + i];
+                            r.x *= sc; r.y *= -sc;
+                            if (j0 + ((q0 + i) << (AL + LM)) < a.n_user)
+                                p[(size_t)(q0 + i) << (AL + LM)] = make_double2(fma(r.x, w[i].x, r.y * w[i].y) * s2, fma(r.y, w[i].x, -(r.x * w[i].y)) * s2);
+                        }
+                    }
+                } else {
+                    cd* p = a.out + ((size_t)tr << LOGN) + ((size_t)kb << LC2) + gl.hi + ((size_t)gl.kloc << LM);
+                    const cd* const fbp = a.fb + ((size_t)kb << LC2) + gl.hi + ((size_t)gl.kloc << LM);
+                    (void)fbp;
+#pragma unroll
+                    for (int q = 0; q < 16; q++) {
+                        cd r = x[q];
+                        if (INV) { r.x *= sc; r.y *= -sc; }
+                        if constexpr (BLUE == FUSED_BLUE_FWD) r = cmul2(r, __ldg(fbp + ((size_t)q << (AL + LM))));   // A * FB (bluestein.c:124-131)
+                        p[(size_t)q << (AL + LM)] = r;
+                    }
                 }
             } else {
                 group_sync(g2);   // every gather is done: stage X[k + M q] in place as [q][k], the box the tensor store expects
@@ -904,6 +971,18 @@ fft_fused_kernel(const FusedArgs a, const __grid_constant__ CUtensorMap tm_in, c
                     for (int q = 0; q < 8; q++) p[q << (AL + LC2)] = x[q];
 #pragma unroll
                     for (int q = 8; q < 16; q++) pm[-(q << (AL + LC2))] = make_double2(x[q].x, -x[q].y);
+                } else if constexpr (BLUE == FUSED_BLUE_FWD) {
+                    // A * FB (bluestein.c:124-131) on the way into the staging buffer; factors fetched four at a time
+                    cd* p = sm + gl.hi + (gl.kloc << LC2);
+                    const cd* const fbp = a.fb + ((size_t)kb << LC2) + gl.hi + ((size_t)gl.kloc << LM);
+#pragma unroll
+                    for (int q0 = 0; q0 < 16; q0 += 4) {
+                        cd w[4];
+#pragma unroll
+                        for (int i = 0; i < 4; i++) w[i] = __ldg(fbp + ((size_t)(q0 + i) << (AL + LM)));
+#pragma unroll
+                        for (int i = 0; i < 4; i++) p[(q0 + i) << (AL + LC2)] = cmul2(x[q0 + i], w[i]);
+                    }
                 } else {
                     cd* p = sm + gl.hi + (gl.kloc << LC2);
 #pragma unroll
@@ -945,6 +1024,17 @@ inline const void* fused_func(int lm, int lr, int inverse) {
     return f;
 }
 const void* fused_cols_func(int inverse);   // column mode (fft_kernels_fused1.cu)
+const void* fused_blue_func_0(int lm, int lr, int kind);
+const void* fused_blue_func_1(int lm, int lr, int kind);
+const void* fused_blue_func_2(int lm, int lr, int kind);
+const void* fused_blue_func_3(int lm, int lr, int kind);
+inline const void* fused_blue_func(int lm, int lr, int kind) {   // kind = FUSED_BLUE_FWD / FUSED_BLUE_INV
+    const void* f = fused_blue_func_0(lm, lr, kind);
+    if (!f) f = fused_blue_func_1(lm, lr, kind);
+    if (!f) f = fused_blue_func_2(lm, lr, kind);
+    if (!f) f = fused_blue_func_3(lm, lr, kind);
+    return f;
+}
 const void* fused_r2c_func_0(int lm, int lr, int herm);
 const void* fused_r2c_func_1(int lm, int lr, int herm);
 const void* fused_r2c_func_2(int lm, int lr, int herm);

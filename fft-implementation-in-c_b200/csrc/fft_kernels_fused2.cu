@@ -20,4 +20,11 @@ const void* fused_r2c_func_2(int lm, int lr, int herm) {
 #undef X
     return nullptr;
 }
+const void* fused_blue_func_2(int lm, int lr, int kind) {
+#define X(A, B) if (lm == A && lr == B) return kind == FUSED_BLUE_FWD ? (const void*)fft_fused_kernel<A, B, false, false, false, false, false, FUSED_BLUE_FWD> \
+                                                                        : (const void*)fft_fused_kernel<A, B, true, false, false, false, false, FUSED_BLUE_INV>;
+    FUSED_PAIRS(X)
+#undef X
+    return nullptr;
+}
 }  // namespace fftb200

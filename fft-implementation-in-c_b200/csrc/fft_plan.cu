@@ -301,6 +301,7 @@ struct fftb200_plan {
     bool c2r_half = false;     // fused C2R that reads the half spectrum itself (no c2r_expand pass, no work array)
     bool fused_c2r = false;    // C2R of 2^14 .. 2^20 points: the fused kernel stores the real parts itself
     bool pipe_blue = false;    // Bluestein with m = 512 .. 4096: both transforms in the pipe kernel's Bluestein variants, no elementwise kernels
+    bool fused_blue = false;   // Bluestein with padded length 2^14 .. 2^20: chirp / FB factors inside the two fused transforms (fft_fused.cuh BLUE)
     bool pipe_real = false;    // R2C / C2R of 512 .. 4096 points: the pipe kernel reads reals / half spectra itself (no work array)
     cd* chirp = nullptr;       // Bluestein: n entries
     cd* fb = nullptr;          // Bluestein: FFT_m of the wrapped chirp
@@ -525,7 +526,8 @@ static unsigned int* sched_counters(fftb200_plan* p) {
     if (!p->sched) {
         p->sched = (unsigned int*)fftb200_malloc(sizeof(unsigned int) * 8);
         if (!p->sched) return nullptr;   // (fftb200_malloc has recorded the error)
-        if (cudaMemset(p->sched, 0, sizeof(unsigned int) * 8) != cudaSuccess) {
+        // (on the plan's stream - it is a non-blocking one, the legacy stream's memset would not be ordered with the kernels)
+        if (cudaMemsetAsync(p->sched, 0, sizeof(unsigned int) * 8, p->stream) != cudaSuccess) {
             cudaFree(p->sched); p->sched = nullptr; cudaGetLastError();
             fail("cudaMemset failed for the tile counters");
             return nullptr;
@@ -535,7 +537,9 @@ static unsigned int* sched_counters(fftb200_plan* p) {
 }
 
 // Enqueue the fused two-pass kernel (fft_fused.cuh) for `nbatch` transforms.
-static int enqueue_fused(fftb200_plan* p, const Pass& ps, const cd* in, cd* out, int inverse, long long nbatch_in, int r2c = 0) {
+// blue = FUSED_BLUE_FWD: `in` is the caller's array (n elements per transform), `out` the work array; FUSED_BLUE_INV: `in` is the work
+// array and `out` the caller's array.
+static int enqueue_fused(fftb200_plan* p, const Pass& ps, const cd* in, cd* out, int inverse, long long nbatch_in, int r2c = 0, int blue = 0) {
     // column mode: a "transform" of the schedule is one 16-column block (2^20 points) of stages 1 .. 16
     const int cols = ps.fused_cols, log_rw = p->log_n - 16, log_cb = cols ? log_rw - 4 : 0;
     const int L = cols ? 20 : p->log_n, lm = ps.fused_lm, lr = ps.fused_lr;
@@ -619,12 +623,25 @@ static int enqueue_fused(fftb200_plan* p, const Pass& ps, const cd* in, cd* out,
                                CU_TENSOR_MAP_SWIZZLE_NONE, pr, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled failed (%d) for the half-spectrum input", (int)r);
     }
+    if (blue == FUSED_BLUE_FWD) {
+        // the caller's rows of n elements as [transform][t < n / R][R]: a quarter of a pass-A tile is the box C x M/4; rows from n / R on are
+        // out of range and arrive as zeros (the padding), the partial row n / R is read by the kernel itself
+        const cuuint64_t hdim[3] = {(cuuint64_t)2 << lr, (cuuint64_t)(p->n >> lr), (cuuint64_t)nbatch};
+        const cuuint64_t hstr[2] = {(cuuint64_t)sizeof(cd) << lr, (cuuint64_t)sizeof(cd) * (cuuint64_t)p->n};
+        const cuuint32_t hbox[3] = {(cuuint32_t)2 << (12 - lm), (cuuint32_t)1 << (lm - 2), 1};
+        const cuuint32_t estr[3] = {1, 1, 1};
+        const CUresult r = enc(&tm[0], CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, (void*)in, hdim, hstr, hbox, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                               CU_TENSOR_MAP_SWIZZLE_NONE, pr, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled failed (%d) for the Bluestein input", (int)r);
+    }
     for (int i = 0; i < 3 && !cols; i++) {
         if (r2c == 1 && i != 1) continue;
         if (c2r_half && i == 0) continue;
+        if (blue == FUSED_BLUE_FWD && i == 0) continue;
         const int lcols = i == 2 ? lm : lr, lrows = i == 2 ? lr : lm;          // row length / rows per transform (log2)
         const long long ntr = i == 1 ? slots * gt : nbatch;
-        void* base = i == 0 ? (void*)in : i == 1 ? (void*)p->fscratch : (void*)out;
+        // (FUSED_BLUE_INV stores from registers: its output map is never used and points at the work array)
+        void* base = i == 0 ? (void*)in : i == 1 ? (void*)p->fscratch : blue == FUSED_BLUE_INV ? (void*)p->work : (void*)out;
         const cuuint64_t gdim[2] = {(cuuint64_t)2 << lcols, (cuuint64_t)ntr << lrows};
         const cuuint64_t gstr[1] = {(cuuint64_t)sizeof(cd) << lcols};
         cuuint32_t box[2] = {(cuuint32_t)2 << (12 - lrows), (cuuint32_t)1 << (lrows - 2)};   // a quarter tile: 1024 elements
@@ -661,6 +678,9 @@ static int enqueue_fused(fftb200_plan* p, const Pass& ps, const cd* in, cd* out,
     fa.scratch = p->fscratch; fa.tab = p->tab; fa.acc = p->acc; fa.flags = p->fflags;
     fa.nbatch = nbatch; fa.gt = (int)gt; fa.ngroups = (int)G; fa.lag = (int)lag; fa.slots = (int)slots;
     fa.inverse = inverse; fa.scale = cols ? 1.0 : p->scale; fa.log_cb = log_cb; fa.out = out; fa.half_in = in;
+    fa.chirp = p->chirp; fa.fb = p->fb; fa.n_user = p->n; fa.y_scale = (blue && p->dir > 0) ? 1.0 / (double)p->n : 1.0;
+    fa.user_in = in; fa.user_out = out;
+    if (blue == FUSED_BLUE_INV) fa.out = p->work;
     fa.debug = getenv("FFTB200_FUSED_DEBUG") ? atoi(getenv("FFTB200_FUSED_DEBUG")) : 0;
     memcpy(fa.dtw, p->fdtw, sizeof(fa.dtw));
     fa.prof = nullptr;
@@ -675,7 +695,8 @@ static int enqueue_fused(fftb200_plan* p, const Pass& ps, const cd* in, cd* out,
     const long long tpa = (r2c == 1 && FUSED_R2C_PACK) ? tpt / 2 : (c2r_half && FUSED_C2R_HALFCOLS) ? tpt / 2 + 1 : tpt;
     const long long items = nbatch * (tpa + (herm ? tpt / 2 + 1 : tpt));   // Hermitian schedule: pass B on the columns k <= M/2 only
     const int grid = (int)(items < ps.grid_max ? items : ps.grid_max);
-    const void* func = r2c == 1 ? fused_r2c_func(lm, lr, herm) : r2c == 2 ? fused_c2r_func(lm, lr, c2r_half) : cols ? fused_cols_func(inverse) : fused_func(lm, lr, inverse);
+    const void* func = blue ? fused_blue_func(lm, lr, blue) : r2c == 1 ? fused_r2c_func(lm, lr, herm) : r2c == 2 ? fused_c2r_func(lm, lr, c2r_half)
+                     : cols ? fused_cols_func(inverse) : fused_func(lm, lr, inverse);
     if (!func) return fail("no fused kernel for 2^%d x 2^%d", lm, lr);
     CU(launch_fused(func, fa, tm, grid, p->stream));
 #ifdef FUSED_PROF
@@ -985,6 +1006,20 @@ extern "C" int fftb200_plan_create(fftb200_plan** out, const fftb200_plan_desc* 
                 p->pipe_blue = true;
                 p->launches = 2;
                 p->desc += " [chirp and spectrum factors inside the two transforms]";
+            }
+            // same box, ms per 2^27 padded points, five kernels / two: m = 2^15 3.59 / 2.60, 2^16 3.54 / 2.32, 2^17 3.69 / 2.55, 2^18 4.00 / 3.73,
+            // 2^19 4.13 / 4.21, 2^20 4.39 / 4.09 (the factor loads sit in the compute groups' path; with three sub-passes per pass there is
+            // little slack for them): m = 2^19 keeps the five kernels
+            if (p->passes.size() == 1 && p->passes[0].fused_lm && !p->passes[0].fused_cols && !getenv("FFTB200_NO_FUSED_BLUE") &&
+                (p->log_n != 19 || getenv("FFTB200_FORCE_FUSED_BLUE"))) {
+                const int lm = p->passes[0].fused_lm, lr = p->passes[0].fused_lr;
+                bool ok = fused_blue_func(lm, lr, FUSED_BLUE_FWD) != nullptr;
+                for (int kind = FUSED_BLUE_FWD; ok && kind <= FUSED_BLUE_INV; kind++)
+                    ok = cudaFuncSetAttribute(fused_blue_func(lm, lr, kind), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FUSED_SMEM) == cudaSuccess;
+                if (!ok) { rc = fail("cudaFuncSetAttribute failed for the fused Bluestein kernels"); break; }
+                p->fused_blue = true;
+                p->launches = 2;
+                p->desc += " [chirp and spectrum factors inside the two fused transforms]";
             }
         }
     } while (0);
@@ -1326,6 +1361,28 @@ static int exec_range(fftb200_plan* p, const void* d_in, void* d_out, long long 
         CU(launch_pipe_real(ps.log_p, PIPE_BLUE_FWD, pa, grid, p->stream));
         pa.in = p->work; pa.out = (cd*)d_out; pa.inverse = 1; pa.scale = p->scale;
         CU(launch_pipe_real(ps.log_p, PIPE_BLUE_INV, pa, grid, p->stream));
+        return 0;
+    }
+    if (p->fused_blue) {
+        if (nbatch <= 0) return 0;
+        const Pass& ps = p->passes[0];
+        const int mode = getenv("FFTB200_FUSED_BLUE_MODE") ? atoi(getenv("FFTB200_FUSED_BLUE_MODE")) : 3;   // bit 0: forward fused, bit 1: inverse fused
+        const double ys = inverse ? 1.0 / (double)p->n : 1.0;
+        if (mode & 1) {
+            if (enqueue_fused(p, ps, (const cd*)d_in, p->work, 0, nbatch, 0, FUSED_BLUE_FWD) != 0) return -1;
+        } else {
+            bluestein_pre_kernel<<<grid_for(total), 256, 0, p->stream>>>(p->work, (const cd*)d_in, p->chirp, p->n, p->m, total);
+            if (enqueue_c2c(p, p->work, p->work, 0, nbatch) != 0) return -1;
+            pointwise_mul_kernel<<<grid_for(total), 256, 0, p->stream>>>(p->work, p->work, p->fb, total, m);
+        }
+        if (mode & 2) {
+            if (enqueue_fused(p, ps, p->work, (cd*)d_out, 1, nbatch, 0, FUSED_BLUE_INV) != 0) return -1;
+        } else {
+            if (enqueue_c2c(p, p->work, p->work, 1, nbatch) != 0) return -1;
+            const size_t tot_out = n * (size_t)nbatch;
+            bluestein_post_kernel<<<grid_for(tot_out), 256, 0, p->stream>>>((cd*)d_out, p->work, p->chirp, p->n, p->m, tot_out, ys);
+        }
+        CU(cudaGetLastError());
         return 0;
     }
     const bool fpre = can_fuse_pre(p), fpost = can_fuse_post(p);
