@@ -376,7 +376,10 @@ static int build_passes(fftb200_plan* p, DeviceState* ds) {
     // (real transforms of 8192 points go to the fused kernel below: it reads reals / half spectra itself - one launch instead of
     // promote / extend + this kernel + extract)
     const bool real13 = (p->kind == FFTB200_R2C || p->kind == FFTB200_C2R) && !getenv("FFTB200_NO_FUSED") && !getenv("FFTB200_REAL13_PIPE");
-    if (L == 13 && !real13 && p->acc && !getenv("FFTB200_NO_PIPE13") && !getenv("FFTB200_NO_PIPE")) {
+    // (and so do the two transforms of a Bluestein plan with padded length 8192: the fused kernel carries the chirp / spectrum factors,
+    // two launches instead of pre + this kernel + product + this kernel + post)
+    const bool blue13 = p->kind == FFTB200_BLUESTEIN && !getenv("FFTB200_NO_FUSED") && !getenv("FFTB200_NO_FUSED_BLUE") && !getenv("FFTB200_BLUE13_PIPE");
+    if (L == 13 && !real13 && !blue13 && p->acc && !getenv("FFTB200_NO_PIPE13") && !getenv("FFTB200_NO_PIPE")) {
         // one visit to shared memory: two 4096-point halves + stage 13 (fft_pipe13.cuh)
         Pass ps;
         ps.k = nullptr; ps.log_p = 13; ps.log_m = 0;

@@ -93,20 +93,24 @@ def test_bluestein_inside_the_pipe_kernel_is_bit_identical(gpu, port, O, n, batc
     assert O.rel_l2(a[rows], np.stack([port.fft(x[r], direction) for r in rows])) <= TOL
 
 
-@pytest.mark.parametrize("n,batch", [(8193, 3), (10000, 37), (16384 - 1, 9), (20011, 5), (65536 + 1, 3), (100003, 2), (262144 - 5, 2), (500009, 1), (524288 - 1, 3)])
+@pytest.mark.parametrize("n,batch", [(2049, 7), (4095, 33), (8193, 3), (10000, 37), (16384 - 1, 9), (20011, 5), (65536 + 1, 3), (100003, 2), (262144 - 5, 2), (500009, 1), (524288 - 1, 3)])
 @pytest.mark.parametrize("direction", [-1, 1])
 def test_bluestein_inside_the_fused_kernel_is_bit_identical(gpu, port, O, n, batch, direction, monkeypatch):
-    """Bluestein with padded length m = 2^14 .. 2^20: the forward transform reads the caller's rows through a tensor map that ends
+    """Bluestein with padded length m = 2^13 .. 2^20: the forward transform reads the caller's rows through a tensor map that ends
     at the last full row (zero padding = out-of-range rows, the partial row read by the kernel), multiplies by conj(chirp) in the
     first gather and by FB before staging; the inverse multiplies by conj(chirp) / n and stores the first n values of every row from
-    registers (fft_fused.cuh, FUSED_BLUE_FWD / INV): 2 launches instead of 5. FFTB200_NO_FUSED_BLUE=1 is the five-kernel path: same
-    arithmetic, identical bits; first and last rows against the oracle; in place. Sizes around every padded length, n a multiple of
+    registers (fft_fused.cuh, FUSED_BLUE_FWD / INV): 2 launches instead of 5. FFTB200_FUSED_BLUE_MODE=0 is the five-kernel path around the
+    same fused transforms: same arithmetic, identical bits; first and last rows against the oracle; in place. Sizes around every padded length, n a multiple of
     the row length R and not, batches that leave ragged groups."""
     x = port.fill(57, 0, n * batch).reshape(batch, n)
     a = gpu.gpu_fft_batch(x, direction)
-    monkeypatch.setenv("FFTB200_NO_FUSED_BLUE", "1")
+    monkeypatch.setenv("FFTB200_FUSED_BLUE_MODE", "0")
     b = gpu.gpu_fft_batch(x, direction)
-    monkeypatch.delenv("FFTB200_NO_FUSED_BLUE")
+    monkeypatch.delenv("FFTB200_FUSED_BLUE_MODE")
+    if 2 * n - 1 > (1 << 18) and 2 * n - 1 <= (1 << 19):   # (2^19 keeps the five kernels by default: force the fused pair)
+        monkeypatch.setenv("FFTB200_FORCE_FUSED_BLUE", "1")
+        a = gpu.gpu_fft_batch(x, direction)
+        monkeypatch.delenv("FFTB200_FORCE_FUSED_BLUE")
     assert np.array_equal(a, b)
     assert np.array_equal(gpu.gpu_fft_batch(x, direction, inplace=True), a)
     rows = sorted({0, batch - 1})
