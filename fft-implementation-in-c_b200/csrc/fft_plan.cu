@@ -787,9 +787,10 @@ static int enqueue_c2c(fftb200_plan* p, const cd* in, cd* out, int inverse, long
         }
         const cd* src = ps.src == BUF_IN ? in : ps.src == BUF_OUT ? out : p->scratch;
         cd* dst = ps.dst == BUF_OUT ? out : p->scratch;
-        // (from 8 transforms per execution: below that the late-stage twiddles come from HBM for most tiles and the tile kernel's
-        // two CTAs per SM hide that better - 2^24: x1 0.323 / 0.308 ms, x4 1.151 / 1.086 ms, x16 4.18 / 4.32 ms ring / tile)
-        if (ps.lastpipe && nbatch >= 8 && !post && !p->peers) {
+        // (from 4 transforms per execution: below that the late-stage twiddles come from HBM for most tiles and the tile kernel's
+        // two CTAs per SM hide that better. With tiles handed out on demand, ring / tile kernel: 2^24 x1 0.327 / 0.312 ms, x2 0.577 / 0.582,
+        // x4 1.072 / 1.113, x16 4.07 / 4.32; 2^23 x4 0.538 / 0.553; 2^22 x4 0.282 / 0.278)
+        if (ps.lastpipe && nbatch >= (getenv("FFTB200_LASTPIPE_MIN") ? atoi(getenv("FFTB200_LASTPIPE_MIN")) : 4) && !post && !p->peers) {
             LastPipeArgs la;
             la.in = src; la.out = dst; la.tab = p->tab;
             la.batch = nbatch; la.log_n = p->log_n; la.log_m = ps.log_m;
