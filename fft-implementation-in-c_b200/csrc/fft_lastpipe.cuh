@@ -105,6 +105,7 @@ __global__ void __launch_bounds__(2 * PIPE_GROUP, 1) fft_lastpipe_kernel(const L
         const int tile = tile_of[b + PIPE_STAGES * (round & 1)];
         if (tile < 0) {   // a closed slot: pass on what this group holds; leave once it has closed a slot of the other group as well
             if (t == 0) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // (the buffer's last readers are ordered before this thread by the barrier it has just waited for)
                 if (issue(next_of[g2], b, round + 1)) told_of[g2] = 1;
                 leave_of[g2] = told_of[g2];
             }

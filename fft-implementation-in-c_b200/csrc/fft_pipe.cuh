@@ -269,6 +269,7 @@ __global__ void __launch_bounds__(2 * PIPE_GROUP, 1) fft_pipe_kernel(const PipeA
             const int tile_k = tile_of[b + PIPE_STAGES * (round & 1)];
             if (tile_k < 0) {   // a closed slot: pass on what this group holds for the slot three ahead; leave once the other group is sure to find a closed slot
                 if (t == 0) {
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // (the buffer's last readers are ordered before this thread by the barrier it has just waited for)
                     if (issue(next_of[g], b, round + 1)) told_of[g] = 1;
                     leave_of[g] = told_of[g];
                 }
