@@ -558,8 +558,10 @@ def main_b200(args, rank, world, local_rank):
                    "parallelism": "batch sharded over %d GPU(s), no collective" % world},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic, "traffic_source": "constant from one `ncu --set full` capture of this kernel "
-                     "(profiles/traffic.json, profiles/r01_n4096_b65536_ncu.md): dram__bytes_read.sum + dram__bytes_write.sum per launch; "
+                     "(profiles/traffic.json, profiles/r02_n4096_b65536_ncu.md): dram__bytes_read.sum + dram__bytes_write.sum per launch; "
                      "NOT measured in this run", "peak_source": peak_src,
+                     "frac_note": "the peak is a copy that gives every SM a fixed share of the data; copies (and this kernel) whose tiles are taken "
+                     "on demand move 6.9-7.1 TB/s on the same chip (tools/copybench.cu, profiles/r02_microbench.md section 5), hence frac > 1",
                      "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": ms / launches_per_step},
         "clocks": clocks, "gpu_launches": launches_per_step * args.steps,
     }
