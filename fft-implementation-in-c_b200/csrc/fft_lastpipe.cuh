@@ -58,7 +58,9 @@ __global__ void __launch_bounds__(2 * PIPE_GROUP, 1) fft_lastpipe_kernel(const L
     int* const next_of = tile_of + 2 * PIPE_STAGES;                        // [2]: the tile a group will load next
     int* const told_of = next_of + 2;                                      // [2]: a slot of the other group has been closed
     int* const leave_of = told_of + 2;                                     // [2]
+    const bool counted = a.ntiles > 3LL * stride;
     auto take = [&]() -> int {
+        if (!counted) return 0x7fffffff;
         const unsigned v = 3u * gridDim.x + atomicAdd(a.sched, 1u);
         return v < 0x7fffffffu ? (int)v : 0x7fffffff;
     };
@@ -187,8 +189,10 @@ __global__ void __launch_bounds__(2 * PIPE_GROUP, 1) fft_lastpipe_kernel(const L
         b += 2;
         if (b >= PIPE_STAGES) { b -= PIPE_STAGES; round++; }
     }
-    __syncthreads();   // every counter read of this CTA has returned: the last CTA to finish resets the counters
-    if (threadIdx.x == 0 && atomicInc(a.sched + 1, gridDim.x - 1) == gridDim.x - 1) a.sched[0] = 0;
+    if (counted) {   // every counter read of this CTA has returned: the last CTA to finish resets the counters
+        __syncthreads();
+        if (threadIdx.x == 0 && atomicInc(a.sched + 1, gridDim.x - 1) == gridDim.x - 1) a.sched[0] = 0;
+    }
 }
 
 constexpr size_t LASTPIPE_SMEM = (size_t)PIPE_STAGES * PIPE_TILE * sizeof(cd) + 128;   // + barriers, tile numbers

@@ -191,7 +191,9 @@ __global__ void __launch_bounds__(2 * PIPE_GROUP, 1) fft_pipe_kernel(const PipeA
     // the counter again - until it has both FOUND a closed slot and CLOSED one itself: then the other group is sure to find a closed
     // slot, and no tile that was handed out is left unloaded. (At most two empty turns per group.)
     // (tile numbers fit 32 bits: 2^31 tiles of 64 KB are more than any memory holds; clamped so that they never wrap)
+    const bool counted = a.ntiles > 3LL * stride;   // small launches (the latency-bound one-shot calls) never touch the counter
     auto take = [&]() -> int {   // the tile of this group's next load
+        if (!counted) return 0x7fffffff;
         const unsigned v = 3u * gridDim.x + atomicAdd(a.sched, 1u);
         return v < 0x7fffffffu ? (int)v : 0x7fffffff;
     };
@@ -467,8 +469,10 @@ __global__ void __launch_bounds__(2 * PIPE_GROUP, 1) fft_pipe_kernel(const PipeA
         if (b >= PIPE_STAGES) { b -= PIPE_STAGES; round++; }
     }
     // every counter read of this CTA has returned (its value was parked or used): the last CTA resets the counters
-    __syncthreads();
-    if (threadIdx.x == 0 && atomicInc(a.sched + 1, gridDim.x - 1) == gridDim.x - 1) a.sched[0] = 0;
+    if (counted) {
+        __syncthreads();
+        if (threadIdx.x == 0 && atomicInc(a.sched + 1, gridDim.x - 1) == gridDim.x - 1) a.sched[0] = 0;
+    }
 }
 
 }  // namespace fftb200

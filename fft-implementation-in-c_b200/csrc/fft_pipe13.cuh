@@ -77,7 +77,9 @@ __global__ void __launch_bounds__(2 * PIPE_GROUP, 1) fft_pipe13_kernel(const Pip
     // position, every later one from the global counter, read at the end of turn k - 1 for turn k + 2, parked in shared memory at the
     // top of turn k (in front of that turn's CTA-wide barriers) and used from turn k's refills on. A number past the end (the counter
     // stays exhausted once it is) ends the CTA at the turn that would have worked on it; halves of such a transform are never loaded.
+    const bool counted = a.ntiles > 2LL * stride;
     auto take = [&]() -> int {
+        if (!counted) return 0x7fffffff;
         const unsigned v = 2u * gridDim.x + atomicAdd(a.sched, 1u);
         return v < 0x7fffffffu ? (int)v : 0x7fffffff;
     };
@@ -229,8 +231,10 @@ __global__ void __launch_bounds__(2 * PIPE_GROUP, 1) fft_pipe13_kernel(const Pip
         b += 2;
         if (b >= PIPE_STAGES) { b -= PIPE_STAGES; round++; }
     }
-    __syncthreads();   // every counter read of this CTA has returned: the last CTA to finish resets the counters
-    if (threadIdx.x == 0 && atomicInc(a.sched + 1, gridDim.x - 1) == gridDim.x - 1) a.sched[0] = 0;
+    if (counted) {   // every counter read of this CTA has returned: the last CTA to finish resets the counters
+        __syncthreads();
+        if (threadIdx.x == 0 && atomicInc(a.sched + 1, gridDim.x - 1) == gridDim.x - 1) a.sched[0] = 0;
+    }
 }
 
 const void* pipe13_func(int inverse);
