@@ -63,6 +63,9 @@
 #ifndef FUSED_C2R_HALFCOLS
 #define FUSED_C2R_HALFCOLS 1
 #endif
+#ifndef FUSED_DYNAMIC
+#define FUSED_DYNAMIC 0
+#endif
 
 namespace fftb200 {
 
@@ -71,6 +74,7 @@ struct FusedArgs {
     const cd* tab;      // reference-recurrence stage tables for size N
     const cd* acc;      // accurate stage tables (stages m <= 8192)
     int* flags;         // [0, G): stored pass-A tiles per group; [G, 2G): loaded pass-B tiles per group
+    int* handout;       // FUSED_DYNAMIC builds: work items handed out beyond the first three of every CTA (its own cache line; zero at launch)
     long long* prof;    // development only (FUSED_PROF builds)
     long long nbatch;
     int gt;             // transforms per group
@@ -464,7 +468,15 @@ fft_fused_kernel(const FusedArgs a, const __grid_constant__ CUtensorMap tm_in, c
     const bool nowait = (a.debug & 7) != 0;
     const long long total = a.nbatch * ((long long)sch.a_on * TPA + (long long)sch.b_on * TPB);
     const int first = blockIdx.x, stride = gridDim.x;
+#if FUSED_DYNAMIC
+    // Experimental (not the product build): work items handed out on demand. A manager takes the first item of its buffer by position
+    // and every later one from a global counter at the moment the buffer's current tile has been staged; a manager that draws a number
+    // past the end closes its buffer twice (once for each compute group, the second time after the first has been acknowledged); a
+    // group skips a buffer it has seen closed and leaves when it has seen all three closed.
+    int* const handout = a.handout;
+#else
     const int my_tiles = first < total ? (int)((total - first + stride - 1) / stride) : 0;
+#endif
 
     if (threadIdx.x == 0) {
 #pragma unroll
@@ -493,7 +505,17 @@ fft_fused_kernel(const FusedArgs a, const __grid_constant__ CUtensorMap tm_in, c
         constexpr int QT = PIPE_TILE / 4;                          // elements per quarter
         constexpr uint32_t QBYTES = QT * (uint32_t)sizeof(cd);
         FusedCursor cur;
+#if FUSED_DYNAMIC
+        auto close_twice = [&](int n) {   // uses n and n + 1 of this buffer: one for each group
+            kinds[4 * w] = -1;
+            mbar_arrive(&full[w]);
+            mbar_wait_bounded(&staged[w], n & 1);   // (the group's acknowledgement)
+            mbar_arrive(&full[w]);
+        };
+        if (first + (long long)w * stride >= total) { close_twice(0); return; }
+#else
         if (w >= my_tiles) return;
+#endif
         FusedItem it = cur.locate(sch, first + (long long)w * stride);
         // issue the four quarter loads of tile `x` into the buffer; WAITQ: quarter q only after the store of quarter q has been read
         auto load = [&](const FusedItem& x, auto waitq) {
@@ -558,12 +580,14 @@ fft_fused_kernel(const FusedArgs a, const __grid_constant__ CUtensorMap tm_in, c
             mp[0] += m1 - m0;
 #endif
             // ---- look ahead: next tile of this buffer, early poll of its dependency; and of this tile's WAR counter ----
+#if !FUSED_DYNAMIC
             const bool have = k + PIPE_STAGES < my_tiles;
             int seen = 0, need = 0;
             if (have) {
                 it = cur.locate(sch, first + (long long)(k + PIPE_STAGES) * stride);
                 if (it.is_b && !nowait) { need = (int)sch.tiles_of(it.g); seen = ld_acquire_gpu(a.flags + it.g); }
             }
+#endif
             int war_need = 0, war_seen = 0;
             const int* war_p = nullptr;
             if (!cur_it.is_b && cur_it.g >= a.slots && !nowait) {
@@ -574,6 +598,9 @@ fft_fused_kernel(const FusedArgs a, const __grid_constant__ CUtensorMap tm_in, c
             }
             // ---- store, one bulk group per quarter ----
             mbar_wait_bounded(&staged[w], n & 1);
+#if FUSED_DYNAMIC
+            const long long next_item = 3LL * stride + (long long)atomicAdd(handout, 1);   // (first needed after the stores have been issued)
+#endif
 #ifdef FUSED_PROF
             const long long m2 = clock64();
             mp[1] += m2 - m1;
@@ -637,6 +664,14 @@ fft_fused_kernel(const FusedArgs a, const __grid_constant__ CUtensorMap tm_in, c
                 }
             }
             // ---- next load, chasing the store quarter by quarter; then publish the store ----
+#if FUSED_DYNAMIC
+            const bool have = next_item < total;
+            int seen = 0, need = 0;
+            if (have) {
+                it = cur.locate(sch, next_item);
+                if (it.is_b && !nowait) { need = (int)sch.tiles_of(it.g); seen = ld_acquire_gpu(a.flags + it.g); }
+            }
+#endif
             if (have) {
                 if (seen >= need) {
                     if (BDIRECT && cur_it.is_b) load(it, nowaitq);   // nothing was stored from this buffer: it is free now
@@ -658,6 +693,9 @@ fft_fused_kernel(const FusedArgs a, const __grid_constant__ CUtensorMap tm_in, c
                 }
             } else {
                 if (!cur_it.is_b) fused_publish(a.flags + cur_it.g);
+#if FUSED_DYNAMIC
+                close_twice(n + 1);
+#endif
                 break;
             }
         }
@@ -676,7 +714,17 @@ fft_fused_kernel(const FusedArgs a, const __grid_constant__ CUtensorMap tm_in, c
     long long pr_e = 0, pr_f = 0, pr_busy[2] = {0, 0}, pr_cnt[2] = {0, 0};
     const long long pr_t0 = clock64();
 #endif
+#if FUSED_DYNAMIC
+    int closed = 0;   // buffers seen closed (bit b)
+    for (;;) {
+        if ((closed >> b) & 1) {
+            b += 2;
+            if (b >= PIPE_STAGES) { b -= PIPE_STAGES; n++; }
+            continue;
+        }
+#else
     for (int k = g2; k < my_tiles; k += 2) {
+#endif
         cd* const sm = bufs + (size_t)b * PIPE_TILE;
 #ifdef FUSED_PROF
         const long long c0 = clock64();
@@ -693,6 +741,17 @@ fft_fused_kernel(const FusedArgs a, const __grid_constant__ CUtensorMap tm_in, c
         pr_e += c1 - c0; pr_f += c2 - c1;
 #endif
         const int is_b = kinds[4 * b], kb = kinds[4 * b + 1];
+#if FUSED_DYNAMIC
+        if (is_b < 0) {   // closed: acknowledge (the manager closes the buffer once more for the other group), leave after the third
+            closed |= 1 << b;
+            __syncwarp();
+            if ((t & 31) == 0) mbar_arrive_cnt(&staged[b], 32);
+            if (closed == (1 << PIPE_STAGES) - 1) break;
+            b += 2;
+            if (b >= PIPE_STAGES) { b -= PIPE_STAGES; n++; }
+            continue;
+        }
+#endif
         const int kg = kinds[4 * b + 2], ktr = kinds[4 * b + 3];   // group and transform within it (read before the buffer is handed back)
         cd x[16];
         if (!is_b) {
@@ -1004,7 +1063,7 @@ fft_fused_kernel(const FusedArgs a, const __grid_constant__ CUtensorMap tm_in, c
 #ifdef FUSED_PROF
     if (t == 0 && a.prof) {
         long long* q = a.prof + (blockIdx.x * 2 + g2) * 4;
-        q[0] = pr_e; q[1] = pr_f; q[2] = clock64() - pr_t0; q[3] = (my_tiles - g2 + 1) / 2;
+        q[0] = pr_e; q[1] = pr_f; q[2] = clock64() - pr_t0; q[3] = pr_cnt[0] + pr_cnt[1];
         long long* q2 = a.prof + 12 * 1024 + (blockIdx.x * 2 + g2) * 4;
         q2[0] = pr_busy[0]; q2[1] = pr_cnt[0]; q2[2] = pr_busy[1]; q2[3] = pr_cnt[1];
     }

@@ -679,6 +679,15 @@ static int enqueue_fused(fftb200_plan* p, const Pass& ps, const cd* in, cd* out,
     }
     FusedArgs fa;
     fa.scratch = p->fscratch; fa.tab = p->tab; fa.acc = p->acc; fa.flags = p->fflags;
+    fa.handout = nullptr;
+#if FUSED_DYNAMIC
+    {
+        unsigned int* sc = sched_counters(p);
+        if (!sc) return -1;
+        fa.handout = reinterpret_cast<int*>(sc + 4);
+        CU(cudaMemsetAsync(fa.handout, 0, sizeof(int), p->stream));
+    }
+#endif
     fa.nbatch = nbatch; fa.gt = (int)gt; fa.ngroups = (int)G; fa.lag = (int)lag; fa.slots = (int)slots;
     fa.inverse = inverse; fa.scale = cols ? 1.0 : p->scale; fa.log_cb = log_cb; fa.out = out; fa.half_in = in;
     fa.chirp = p->chirp; fa.fb = p->fb; fa.n_user = p->n; fa.y_scale = (blue && p->dir > 0) ? 1.0 / (double)p->n : 1.0;
