@@ -398,8 +398,8 @@ __device__ __forceinline__ void fused_publish(int* counter) {
 // BLUE = FUSED_BLUE_FWD / FUSED_BLUE_INV: the two transforms of Bluestein's algorithm (bluestein.c:107-148) for padded lengths
 // N = 2^14 .. 2^20 with the elementwise steps riding on them, as in fft_pipe_kernel for N <= 4096. FWD: pass A reads the caller's rows
 // of n_user elements through a 3-D tensor map whose rows end at the last full row of R elements (the rows behind it arrive as zeros:
-// the padding; the partial row is read from the caller's array in the first gather), multiplies by conj(chirp) in the first gather, and
-// pass B multiplies the spectrum by FB before it is staged. INV (inverse transform, 1/N): pass B multiplies by conj(chirp) * y_scale and
+// the padding; the partial row is read from the caller's array in the first gather) and multiplies by conj(chirp) in the first gather.
+// INV (inverse transform, 1/N): pass A multiplies the spectrum by FB in its first gather, pass B multiplies by conj(chirp) * y_scale and
 // stores the first n_user values of every row from registers to the caller's array. Two launches and HBM round trips instead of five,
 // the same arithmetic as bluestein_pre / pointwise_mul / bluestein_post (fft_aux.cuh).
 enum { FUSED_BLUE_NONE = 0, FUSED_BLUE_FWD = 1, FUSED_BLUE_INV = 2 };
@@ -806,6 +806,23 @@ fft_fused_kernel(const FusedArgs a, const __grid_constant__ CUtensorMap tm_in, c
                         SubStageExact<RA0, 1, 0, 0>::run(&x[bb * R0]);
                         fused_scatter<G0, SwzId, RA0>(&x[bb * R0], sm, g);
                     }
+                } else if constexpr (BLUE == FUSED_BLUE_INV) {
+                    // A * FB (bluestein.c:124-131) on the way in, then the conjugate of the inverse transform: element (t, c) of the tile is A[c + R t].
+                    // (The product rides here and not on the forward transform's staging: there it costs 270 bytes of spills at 2^10 x 2^9.)
+#pragma unroll
+                    for (int bb = 0; bb < NB; bb++) {
+                        const G0 g(t + PIPE_GROUP * bb);
+                        const int base = g.gbase();
+#pragma unroll
+                        for (int rho = 0; rho < R0; rho++) {
+                            const int I = base + rho * G0::GSTRIDE;
+                            const int i = (kb << LC) + (I & ((1 << LC) - 1)) + ((I >> LC) << LR);
+                            const cd y = cmul2(sm[I], __ldg(a.fb + i));
+                            x[bb * R0 + bitrev_c<RA0>(rho)] = make_double2(y.x, -y.y);
+                        }
+                        SubStageExact<RA0, 1, 0, 0>::run(&x[bb * R0]);
+                        fused_scatter<G0, SwzId, RA0>(&x[bb * R0], sm, g);
+                    }
                 } else {
 #pragma unroll
                     for (int bb = 0; bb < NB; bb++) {
@@ -1006,13 +1023,10 @@ fft_fused_kernel(const FusedArgs a, const __grid_constant__ CUtensorMap tm_in, c
                     }
                 } else {
                     cd* p = a.out + ((size_t)tr << LOGN) + ((size_t)kb << LC2) + gl.hi + ((size_t)gl.kloc << LM);
-                    const cd* const fbp = a.fb + ((size_t)kb << LC2) + gl.hi + ((size_t)gl.kloc << LM);
-                    (void)fbp;
 #pragma unroll
                     for (int q = 0; q < 16; q++) {
                         cd r = x[q];
                         if (INV) { r.x *= sc; r.y *= -sc; }
-                        if constexpr (BLUE == FUSED_BLUE_FWD) r = cmul2(r, __ldg(fbp + ((size_t)q << (AL + LM))));   // A * FB (bluestein.c:124-131)
                         p[(size_t)q << (AL + LM)] = r;
                     }
                 }
@@ -1030,18 +1044,6 @@ fft_fused_kernel(const FusedArgs a, const __grid_constant__ CUtensorMap tm_in, c
                     for (int q = 0; q < 8; q++) p[q << (AL + LC2)] = x[q];
 #pragma unroll
                     for (int q = 8; q < 16; q++) pm[-(q << (AL + LC2))] = make_double2(x[q].x, -x[q].y);
-                } else if constexpr (BLUE == FUSED_BLUE_FWD) {
-                    // A * FB (bluestein.c:124-131) on the way into the staging buffer; factors fetched four at a time
-                    cd* p = sm + gl.hi + (gl.kloc << LC2);
-                    const cd* const fbp = a.fb + ((size_t)kb << LC2) + gl.hi + ((size_t)gl.kloc << LM);
-#pragma unroll
-                    for (int q0 = 0; q0 < 16; q0 += 4) {
-                        cd w[4];
-#pragma unroll
-                        for (int i = 0; i < 4; i++) w[i] = __ldg(fbp + ((size_t)(q0 + i) << (AL + LM)));
-#pragma unroll
-                        for (int i = 0; i < 4; i++) p[(q0 + i) << (AL + LC2)] = cmul2(x[q0 + i], w[i]);
-                    }
                 } else {
                     cd* p = sm + gl.hi + (gl.kloc << LC2);
 #pragma unroll

@@ -1020,11 +1020,9 @@ extern "C" int fftb200_plan_create(fftb200_plan** out, const fftb200_plan_desc* 
                 p->launches = 2;
                 p->desc += " [chirp and spectrum factors inside the two transforms]";
             }
-            // same box, ms per 2^27 padded points, five kernels / two: m = 2^15 3.59 / 2.60, 2^16 3.54 / 2.32, 2^17 3.69 / 2.55, 2^18 4.00 / 3.73,
-            // 2^19 4.13 / 4.21, 2^20 4.39 / 4.09 (the factor loads sit in the compute groups' path; with three sub-passes per pass there is
-            // little slack for them): m = 2^19 keeps the five kernels
-            if (p->passes.size() == 1 && p->passes[0].fused_lm && !p->passes[0].fused_cols && !getenv("FFTB200_NO_FUSED_BLUE") &&
-                (p->log_n != 19 || getenv("FFTB200_FORCE_FUSED_BLUE"))) {
+            // same box, ms per 2^27 padded points, five kernels / two: m = 2^13 3.56 / 2.27, 2^14 3.69 / 2.43, 2^15 3.59 / 2.45, 2^16 3.50 / 2.26,
+            // 2^17 3.69 / 2.55, 2^18 3.99 / 3.11, 2^19 4.13 / 3.70, 2^20 4.38 / 3.84
+            if (p->passes.size() == 1 && p->passes[0].fused_lm && !p->passes[0].fused_cols && !getenv("FFTB200_NO_FUSED_BLUE")) {
                 const int lm = p->passes[0].fused_lm, lr = p->passes[0].fused_lr;
                 bool ok = fused_blue_func(lm, lr, FUSED_BLUE_FWD) != nullptr;
                 for (int kind = FUSED_BLUE_FWD; ok && kind <= FUSED_BLUE_INV; kind++)

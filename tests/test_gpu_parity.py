@@ -97,9 +97,9 @@ def test_bluestein_inside_the_pipe_kernel_is_bit_identical(gpu, port, O, n, batc
 @pytest.mark.parametrize("direction", [-1, 1])
 def test_bluestein_inside_the_fused_kernel_is_bit_identical(gpu, port, O, n, batch, direction, monkeypatch):
     """Bluestein with padded length m = 2^13 .. 2^20: the forward transform reads the caller's rows through a tensor map that ends
-    at the last full row (zero padding = out-of-range rows, the partial row read by the kernel), multiplies by conj(chirp) in the
-    first gather and by FB before staging; the inverse multiplies by conj(chirp) / n and stores the first n values of every row from
-    registers (fft_fused.cuh, FUSED_BLUE_FWD / INV): 2 launches instead of 5. FFTB200_FUSED_BLUE_MODE=0 is the five-kernel path around the
+    at the last full row (zero padding = out-of-range rows, the partial row read by the kernel) and multiplies by conj(chirp) in the
+    first gather; the inverse multiplies by FB in its first gather and by conj(chirp) / n on the way out, storing the first n values of
+    every row from registers (fft_fused.cuh, FUSED_BLUE_FWD / INV): 2 launches instead of 5. FFTB200_FUSED_BLUE_MODE=0 is the five-kernel path around the
     same fused transforms: same arithmetic, identical bits; first and last rows against the oracle; in place. Sizes around every padded length, n a multiple of
     the row length R and not, batches that leave ragged groups."""
     x = port.fill(57, 0, n * batch).reshape(batch, n)
@@ -107,10 +107,6 @@ def test_bluestein_inside_the_fused_kernel_is_bit_identical(gpu, port, O, n, bat
     monkeypatch.setenv("FFTB200_FUSED_BLUE_MODE", "0")
     b = gpu.gpu_fft_batch(x, direction)
     monkeypatch.delenv("FFTB200_FUSED_BLUE_MODE")
-    if 2 * n - 1 > (1 << 18) and 2 * n - 1 <= (1 << 19):   # (2^19 keeps the five kernels by default: force the fused pair)
-        monkeypatch.setenv("FFTB200_FORCE_FUSED_BLUE", "1")
-        a = gpu.gpu_fft_batch(x, direction)
-        monkeypatch.delenv("FFTB200_FORCE_FUSED_BLUE")
     assert np.array_equal(a, b)
     assert np.array_equal(gpu.gpu_fft_batch(x, direction, inplace=True), a)
     rows = sorted({0, batch - 1})

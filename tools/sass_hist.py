@@ -22,11 +22,13 @@ for line in out.splitlines():
     m = re.match(r"\s*/\*[0-9a-f]{4}\*/\s+(?:@!?U?P\d+\s+)?([A-Z][A-Z0-9_]*(?:\.[A-Z0-9_]+)*)", line)
     if m and cur:
         fam[cur][m.group(1).split(".")[0]] += 1
-KEY = ["UBLKCP", "UTMALDG", "UTMASTG", "UTMACMDFLUSH", "SYNCS", "DFMA", "DMUL", "DADD", "LDS", "STS", "LDG", "STG", "BAR", "SHFL", "UTCHMMA", "UTCQMMA", "HMMA", "LDTM", "ATOMG", "RED", "MEMBAR", "FENCE", "LDL", "STL"]
+KEY = ["UBLKCP", "UTMALDG", "UTMASTG", "UTMACMDFLUSH", "SYNCS", "DFMA", "DMUL", "DADD", "LDS", "STS", "LDG", "STG", "BAR", "SHFL", "UTCHMMA", "UTCQMMA", "HMMA", "LDTM", "STTM", "UTCATOMSWS", "ATOMG", "RED", "MEMBAR", "FENCE", "LDL", "STL"]
 print("# r02 - SASS opcode histogram of fft-implementation-in-c_b200/lib/libfft_b200.so (tools/sass_hist.py, cuobjdump -sass)\n")
 print("cubins by architecture:", dict(archs), "\n")
 print("Instances = template instantiations of the kernel in the library; counts are static instructions summed over them. UBLKCP = 1-D bulk async copy, UTMALDG / UTMASTG = TMA tensor")
-print("load / store, SYNCS = mbarrier operations, LDL / STL = local-memory (spill) traffic. No UTC*MMA / HMMA / LDTM: FP64 Stockham butterflies have no tensor-core path on sm_100a.\n")
+print("load / store, SYNCS = mbarrier operations, LDL / STL = local-memory (spill) traffic, ATOMG = global atomics (dependency counters of the fused kernel, tile hand-out counters of the ring")
+print("kernels). No UTC*MMA / HMMA: FP64 Stockham butterflies have no tensor-core path on sm_100a. LDTM / STTM / UTCATOMSWS = tensor-memory loads / stores / allocation: only in the opt-in")
+print("8192-point variant fft_pipe13t_kernel, which uses tensor memory as a parking space, not for MMA accumulators.\n")
 print("| kernel | instances | " + " | ".join(KEY) + " | total |")
 print("|---|---|" + "|".join(["---"] * (len(KEY) + 1)) + "|")
 for k in sorted(fam, key=lambda k: -sum(fam[k].values())):
