@@ -66,6 +66,28 @@
 #ifndef FUSED_DYNAMIC
 #define FUSED_DYNAMIC 0
 #endif
+// FUSED_REGS > 0: the manager warps give registers to the compute warps (setmaxnreg). The CTA gets a fourth (idle) manager warp so that the
+// managers are a whole warpgroup and starts at 96 registers per thread (640 threads); the managers drop to FUSED_MGR_REGS and the compute
+// warps rise to FUSED_REGS. The registers come out of the CTA's own pool (640 x 96 = 61440: an increase beyond what the managers released
+// blocks for ever - 112 / 40 did), so 128 x FUSED_MGR_REGS + 512 x FUSED_REGS <= 61440. At 104 the compute code of every variant but a few
+// real / Bluestein ones is free of spills (24-88 bytes of stack at 96). Same box, ms per 2^28 points, 96 -> 104 registers: 2^14 2.34 -> 2.16,
+// 2^15 2.37 -> 2.17, 2^16 2.25 -> 2.26, 2^17 2.41 -> 2.27, 2^18 2.66 -> 2.60, 2^19 2.78 -> 2.66, 2^20 2.90 -> 2.85, 2^24 x 16 4.07 -> 3.98.
+// 112 with managers at 32 (they spill): the same within noise. Round 2's first half tried 104 by other means and saw nothing.
+#ifndef FUSED_REGS
+#define FUSED_REGS 104
+#endif
+#ifndef FUSED_MGR_REGS
+#define FUSED_MGR_REGS 56
+#endif
+static_assert(FUSED_REGS == 0 || 128 * FUSED_MGR_REGS + 512 * FUSED_REGS <= 640 * 96, "setmaxnreg: the compute warps can only take what the managers release");
+// FUSED_TW_AHEAD: the four table twiddles of a pass-B sub-pass are requested right after the butterflies of the sub-pass before (one
+// exchange ahead of their use); lost at 96 registers per thread (round 2, first half) and again at 104 / 112 (2^15 2.17 -> 2.23, 2^17 2.27 -> 2.30,
+// 2^18 2.63 -> 2.56, 2^19 2.66 -> 2.70, the rest equal): off
+#ifndef FUSED_TW_AHEAD
+#define FUSED_TW_AHEAD 0
+#endif
+#define FUSED_STR2(x) #x
+#define FUSED_STR(x) FUSED_STR2(x)
 
 namespace fftb200 {
 
@@ -97,7 +119,7 @@ struct FusedArgs {
     cd dtw[3][16];      // pass B, sub-pass j: dtw[j][h] = T[stage][q << a_tot] (table entry at kappa = 0), h = 2^(s-1) + q
 };
 
-constexpr int FUSED_THREADS = 2 * PIPE_GROUP + 32 * PIPE_STAGES;   // two compute groups + one manager warp per ring buffer
+constexpr int FUSED_THREADS = 2 * PIPE_GROUP + 32 * (FUSED_REGS ? 4 : PIPE_STAGES);   // two compute groups + one manager warp per ring buffer
 constexpr int FUSED_TW1 = 16 * 8, FUSED_TW2 = 64 * 8;
 constexpr int FUSED_ROWH = 64;   // r2c: the pass-A row k = M/2 of a tile (2C <= 64 complex), staged beside each ring buffer
 constexpr size_t FUSED_SMEM = (size_t)PIPE_STAGES * PIPE_TILE * sizeof(cd) + (FUSED_TW1 + FUSED_TW2 + PIPE_STAGES * FUSED_ROWH) * sizeof(cd) + 256;
@@ -498,8 +520,11 @@ fft_fused_kernel(const FusedArgs a, const __grid_constant__ CUtensorMap tm_in, c
     // Dependency counters are polled early (while the buffer is busy) and only waited for at points where
     // nothing this CTA owes to others is pending in the buffer.
     if (threadIdx.x >= 2 * PIPE_GROUP) {
+#if FUSED_REGS
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 " FUSED_STR(FUSED_MGR_REGS) ";");
+#endif
         const int w = (threadIdx.x - 2 * PIPE_GROUP) >> 5;
-        if ((threadIdx.x & 31) != 0) return;
+        if ((threadIdx.x & 31) != 0 || w >= PIPE_STAGES) return;
         const uint64_t pol_first = policy_evict_first(), pol_last = policy_evict_last();
         cd* const buf = bufs + (size_t)w * PIPE_TILE;
         constexpr int QT = PIPE_TILE / 4;                          // elements per quarter
@@ -707,6 +732,9 @@ fft_fused_kernel(const FusedArgs a, const __grid_constant__ CUtensorMap tm_in, c
     }
 
     // =========================== compute groups ===========================
+#if FUSED_REGS
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 " FUSED_STR(FUSED_REGS) ";");
+#endif
     const int g2 = threadIdx.x / PIPE_GROUP, t = threadIdx.x % PIPE_GROUP;
     const double sc = a.scale;
     int b = g2, n = 0;   // ring buffer and use count of tile k = g2, g2 + 2, ... (b = k % 3, n = k / 3)
@@ -935,6 +963,9 @@ fft_fused_kernel(const FusedArgs a, const __grid_constant__ CUtensorMap tm_in, c
             typedef Geo<0, LR, LC2, AL, 4, true> GL;      // last sub-pass
             const G1 g1(t);
             const GL gl(t);
+#if FUSED_TW_AHEAD
+            cd raw_next[4];   // table twiddles of the next sub-pass, in flight across the exchange
+#endif
             {
                 typedef Geo<0, LR, LC2, 0, RB0, false> G0;
                 constexpr int NB = 16 >> RB0, R0 = 1 << RB0;
@@ -970,6 +1001,10 @@ fft_fused_kernel(const FusedArgs a, const __grid_constant__ CUtensorMap tm_in, c
                     fused_twiddles<RB0>(tw, a.tab + ((kb << LC2) + g.hi - 1), LM, a.dtw[0]);
                     SubStageGen<RB0, 1, 0, 0>::run(&x[bb * R0], tw);
                 }
+#if FUSED_TW_AHEAD
+                if constexpr (B3) fused_tw_load<4>(raw_next, a.tab + ((kb << LC2) + g1.hi + (g1.kloc << LM) - 1), LM + RB0);
+                else fused_tw_load<4>(raw_next, a.tab + ((kb << LC2) + gl.hi + (gl.kloc << LM) - 1), LM + AL);
+#endif
                 group_sync(g2);   // every gather of sub-pass 0 is done (the layout changes)
 #pragma unroll
                 for (int bb = 0; bb < NB; bb++) {
@@ -982,9 +1017,16 @@ fft_fused_kernel(const FusedArgs a, const __grid_constant__ CUtensorMap tm_in, c
                 fused_gather<G1, SW1, 4, false>(x, sm, g1);
                 {
                     cd tw[16];
+#if FUSED_TW_AHEAD
+                    fused_tw_expand<4>(tw, raw_next, a.dtw[1]);
+#else
                     fused_twiddles<4>(tw, a.tab + ((kb << LC2) + g1.hi + (g1.kloc << LM) - 1), LM + RB0, a.dtw[1]);
+#endif
                     SubStageGen<4, 1, 0, 0>::run(x, tw);
                 }
+#if FUSED_TW_AHEAD
+                fused_tw_load<4>(raw_next, a.tab + ((kb << LC2) + gl.hi + (gl.kloc << LM) - 1), LM + AL);
+#endif
                 group_sync(g2);
                 fused_scatter<G1, SWL, 4>(x, sm, g1);
                 group_sync(g2);
@@ -993,7 +1035,11 @@ fft_fused_kernel(const FusedArgs a, const __grid_constant__ CUtensorMap tm_in, c
             if constexpr (BDIRECT) fused_stage_done(&staged[b], t);   // this warp has read its part: the buffer goes back when all have
             {
                 cd tw[16];
+#if FUSED_TW_AHEAD
+                fused_tw_expand<4>(tw, raw_next, a.dtw[2]);
+#else
                 fused_twiddles<4>(tw, a.tab + ((kb << LC2) + gl.hi + (gl.kloc << LM) - 1), LM + AL, a.dtw[2]);
+#endif
                 SubStageGen<4, 1, 0, 0>::run(x, tw);
             }
             if constexpr (BDIRECT) {
