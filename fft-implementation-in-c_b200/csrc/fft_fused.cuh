@@ -40,7 +40,8 @@
 // fence takes as long as the outstanding stores need to drain); all 15 twiddles of a pass-B butterfly loaded
 // instead of 4 + 11 derived 2.68; whole-buffer instead of quarter-wise store -> load hand-over 2.28; L2 prefetch
 // (cp.async.bulk.prefetch.tensor) of the next pass-A tile 2.37; 104 instead of 96 registers for the compute
-// warps (setmaxnreg) 2.32. What bounds it: a 64 KB tile occupies shared memory for its load latency + ~4500-7000
+// warps (setmaxnreg) 2.32 at 2^16 in round 1 - the rebalancing is in the product since the end of round 2 (FUSED_REGS below: 2^16 is the
+// one size it does not move; 2^14, 2^15, 2^17, 2^19 gain 3-8 %). What bounds it: a 64 KB tile occupies shared memory for its load latency + ~4500-7000
 // cycles of compute + its store read-out, and only three tiles fit, so the SM <-> L2 interface (measured with
 // tools/l2bench.cu: TMA stores 26 B/clk/SM, loads 69 B/clk/SM) idles about half of the time.
 #pragma once
@@ -473,7 +474,10 @@ fft_fused_kernel(const FusedArgs a, const __grid_constant__ CUtensorMap tm_in, c
     // the store drain into the compute group's time. Same-box A/B at 2^28 points (ms, direct vs staged): 2^13 2.61 / 2.24,
     // 2^14 2.34 / 2.62, 2^15 2.34 / 2.59, 2^16 2.35 / 2.26, 2^17 2.55 / 2.50, 2^18 3.04 / 2.77, 2^19 3.00 / 2.79,
     // 2^20 3.39 / 2.95: it pays only for LR = 7 (rows of 32 elements, two sub-passes), which is where it is used.
-    constexpr bool BDIRECT = (FUSED_BDIRECT && !COLS && !R2C && !C2R && LR == 7) || BLUE == FUSED_BLUE_INV;   // (the caller's rows of n_user elements cannot be a tensor box)
+#ifndef FUSED_BDIRECT_MAXLR
+#define FUSED_BDIRECT_MAXLR 7
+#endif
+    constexpr bool BDIRECT = (FUSED_BDIRECT && !COLS && !R2C && !C2R && LR >= 7 && LR <= FUSED_BDIRECT_MAXLR) || BLUE == FUSED_BLUE_INV;   // (the caller's rows of n_user elements cannot be a tensor box)
 
     extern __shared__ __align__(128) unsigned char smem_raw[];
     cd* const bufs = reinterpret_cast<cd*>(smem_raw);
