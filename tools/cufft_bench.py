@@ -51,8 +51,12 @@ for tag, n, batch in cases:
     want = p.fft(p.fill(43, (batch - 1) * n, n), -1)
     e_cu = O.rel_l2(y[batch - 1].cpu().numpy(), want)
     kind = F.FFTB200_C2C if n & (n - 1) == 0 else F.FFTB200_BLUESTEIN
+    torch.cuda.empty_cache()   # (the output cuFFT allocated for itself goes back to the driver: both sides run with x and y only)
     t_we, desc = ours(n, batch, kind, x.data_ptr(), y.data_ptr())
     e_we = O.rel_l2(y[batch - 1].cpu().numpy(), want)
+    # second round in the other order (the box is power-capped: whoever runs second inherits the other's clocks); best of both rounds
+    t_we = min(t_we, ours(n, batch, kind, x.data_ptr(), y.data_ptr())[0])
+    t_cu = min(t_cu, ev_time(lambda: torch.fft.fft(x, out=y)))
     b = 32.0 * n * batch
     print("| %s | %d | %d | %.4f | %.4f | %.2fx | %.0f (%.2f) | %.0f (%.2f) | %.1e | %.1e | %s |" % (tag, n, batch, t_cu, t_we, t_cu / t_we, b / t_cu * 1e-6, b / t_cu * 1e-6 / peak,
           b / t_we * 1e-6, b / t_we * 1e-6 / peak, e_cu, e_we, desc), flush=True)
