@@ -28,12 +28,22 @@ struct LastPipeArgs {
     int inverse;
     double scale;       // applied with the final conjugation when inverse
     unsigned int* sched;   // tile hand-out counters (fft_pipe.cuh "Tile order"): [0] tiles taken beyond the first three per CTA, [1] CTAs finished
+    // derive != 0: of the 2^R - 1 twiddles of a radix-2^R butterfly only the R entries T[a + s][kappa] are loaded, the others are the product
+    // with dtw[j][h] = T[a + s][q << a], the table's own entry at kappa = 0 (fft_fused.cuh fused_twiddles: the reference's recurrence is
+    // multiplicative up to rounding noise): a quarter of the table traffic, which for the last stages is as many bytes as the data
+    int derive;
+    cd dtw[3][16];         // sub-pass j (first / middle / last): a = log_m, log_m + RB0, log_m + LR - 4
 };
 
 template <int R>
 __device__ __forceinline__ void table_twiddles(cd* tw, const cd* tp, const int a_tot) {
 #pragma unroll
     for (int h = 1; h < (1 << R); h++) tw[h] = __ldg(tp + ((size_t)h << a_tot));
+}
+template <int R>
+__device__ __forceinline__ void last_twiddles(cd* tw, const cd* tp, const int a_tot, const int derive, const cd* d) {
+    if (derive) fused_twiddles<R>(tw, tp, a_tot, d);
+    else table_twiddles<R>(tw, tp, a_tot);
 }
 
 template <int LR, bool INV>
@@ -135,7 +145,7 @@ __global__ void __launch_bounds__(2 * PIPE_GROUP, 1) fft_lastpipe_kernel(const L
 #pragma unroll
             for (int bb = 0; bb < NB; bb++) {
                 const G0 g(t + PIPE_GROUP * bb);
-                table_twiddles<RB0>(tw, a.tab + ((kb << LC2) + g.hi - 1), lm);
+                last_twiddles<RB0>(tw, a.tab + ((kb << LC2) + g.hi - 1), lm, a.derive, a.dtw[0]);
                 SubStageGen<RB0, 1, 0, 0>::run(&x[bb * R0], tw);
             }
             group_sync(g2);   // every gather of sub-pass 0 is done (the layout changes)
@@ -152,7 +162,7 @@ __global__ void __launch_bounds__(2 * PIPE_GROUP, 1) fft_lastpipe_kernel(const L
             fused_gather<G1, SW1, 4, false>(x, sm, g1);
             {
                 cd tw[16];
-                table_twiddles<4>(tw, a.tab + ((kb << LC2) + g1.hi + ((size_t)g1.kloc << lm) - 1), lm + RB0);
+                last_twiddles<4>(tw, a.tab + ((kb << LC2) + g1.hi + ((size_t)g1.kloc << lm) - 1), lm + RB0, a.derive, a.dtw[1]);
                 SubStageGen<4, 1, 0, 0>::run(x, tw);
             }
             group_sync(g2);
@@ -171,7 +181,7 @@ __global__ void __launch_bounds__(2 * PIPE_GROUP, 1) fft_lastpipe_kernel(const L
             // (asking for these 15 entries before the exchange settles - they only depend on the tile and the thread - spills
             // 190 bytes and is slower: 4.49 vs 4.21 ms at 2^24 x 16)
             cd tw[16];
-            table_twiddles<4>(tw, a.tab + ((kb << LC2) + gl.hi + ((size_t)gl.kloc << lm) - 1), lm + AL);
+            last_twiddles<4>(tw, a.tab + ((kb << LC2) + gl.hi + ((size_t)gl.kloc << lm) - 1), lm + AL, a.derive, a.dtw[2]);
             SubStageGen<4, 1, 0, 0>::run(x, tw);
         }
         {

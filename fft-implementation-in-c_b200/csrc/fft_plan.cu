@@ -291,6 +291,8 @@ struct fftb200_plan {
     unsigned int* sched = nullptr;   // persistent kernels: tile hand-out counters (zero between launches, the kernels reset them)
     size_t fflags_count = 0;
     cd fdtw[3][16];            // fused plans: pass-B derived-twiddle constants (fft_fused.cuh: fused_twiddles)
+    cd ldtw[3][16];            // the same for the last pass in the ring kernel (fft_lastpipe.cuh: derive)
+    bool last_derive = false;
     cd* own_tab = nullptr;     // partial plans with a private (rank-specific) twiddle table
     cd** peers = nullptr;      // partial plans whose last pass stores into the peers' exchange buffers (device array of G pointers)
     int peer_lw = 0, peer_lrows = 0, peer_lg = 0, peer_me = 0;
@@ -796,10 +798,12 @@ static int enqueue_c2c(fftb200_plan* p, const cd* in, cd* out, int inverse, long
         }
         const cd* src = ps.src == BUF_IN ? in : ps.src == BUF_OUT ? out : p->scratch;
         cd* dst = ps.dst == BUF_OUT ? out : p->scratch;
-        // (from 4 transforms per execution: below that the late-stage twiddles come from HBM for most tiles and the tile kernel's
-        // two CTAs per SM hide that better. With tiles handed out on demand, ring / tile kernel: 2^24 x1 0.327 / 0.312 ms, x2 0.577 / 0.582,
-        // x4 1.072 / 1.113, x16 4.07 / 4.32; 2^23 x4 0.538 / 0.553; 2^22 x4 0.282 / 0.278)
-        if (ps.lastpipe && nbatch >= (getenv("FFTB200_LASTPIPE_MIN") ? atoi(getenv("FFTB200_LASTPIPE_MIN")) : 4) && !post && !p->peers) {
+        // With every twiddle from the table the ring kernel pays from 4 transforms per execution (below that the late-stage twiddles come from
+        // HBM for most tiles and the tile kernel's two CTAs per SM hide that better: 2^24 x1 0.327 / 0.312 ms ring / tile). With derived twiddles
+        // it pays from one transform for P = 128, 256 (2^24 x1 0.295 / 0.308, x2 0.538 / 0.566, x3 0.783 / 0.830; 2^23 x1 0.164 / 0.166,
+        // x3 0.402 / 0.412) and from 8 for P = 64 (2^22 x2 0.161 / 0.156, x3 0.220 / 0.216).
+        const long long ring_from = getenv("FFTB200_LASTPIPE_MIN") ? atoi(getenv("FFTB200_LASTPIPE_MIN")) : p->last_derive ? (ps.log_p <= 6 ? 8 : 1) : 4;
+        if (ps.lastpipe && nbatch >= ring_from && !post && !p->peers) {
             LastPipeArgs la;
             la.in = src; la.out = dst; la.tab = p->tab;
             la.batch = nbatch; la.log_n = p->log_n; la.log_m = ps.log_m;
@@ -807,6 +811,8 @@ static int enqueue_c2c(fftb200_plan* p, const cd* in, cd* out, int inverse, long
             la.inverse = inverse; la.scale = p->scale;
             la.sched = sched_counters(p);
             if (!la.sched) return -1;
+            la.derive = p->last_derive ? 1 : 0;
+            memcpy(la.dtw, p->ldtw, sizeof(la.dtw));
             CU(launch_lastpipe(ps.log_p, la, (int)(la.ntiles < ps.lastpipe ? la.ntiles : ps.lastpipe), p->stream));
             continue;
         }
@@ -946,6 +952,24 @@ extern "C" int fftb200_plan_create(fftb200_plan** out, const fftb200_plan_desc* 
                     p->fdtw[j][h] = make_double2(1.0, 0.0);
                     if (h >= 1 && h < (1 << rad[j]) && !(j == 1 && lr < 9)) p->fdtw[j][h] = ht[((size_t)h << atot[j]) - 1];
                 }
+        }
+        // Derived twiddles in the last pass (fft_lastpipe.cuh `derive`): a quarter of the table traffic. The product T[kappa] * T[q << a] reproduces
+        // the systematic drift of the reference's recurrence but not its rounding noise, which grows with the length of the recurrence: measured
+        // against the all-table kernel 2.9e-14 at 2^22, 7.5e-14 at 2^23, 2.9e-13 at 2^24 - and past the 1e-12 bar at 2^26. Used up to 2^24.
+        if (!p->passes.empty() && p->passes.back().lastpipe && p->log_n <= 24 && d->twiddles && d->table_n >= p->m && !getenv("FFTB200_LASTPIPE_TABLE")) {
+            // ldtw[j][h] = table entry (h << a_j) - 1 (stage a_j + s, index q << a_j, h = 2^(s-1) + q)
+            const Pass& lp = p->passes.back();
+            const int lr = lp.log_p, rb0 = lr >= 9 ? lr - 8 : lr - 4;
+            const int atot[3] = {lp.log_m, lp.log_m + rb0, lp.log_m + lr - 4};
+            const int rad[3] = {rb0, 4, 4};
+            const cd* ht = (const cd*)d->twiddles;
+            for (int j = 0; j < 3; j++)
+                for (int h = 0; h < 16; h++) {
+                    p->ldtw[j][h] = make_double2(1.0, 0.0);
+                    if (h >= 1 && h < (1 << rad[j]) && !(j == 1 && lr < 9)) p->ldtw[j][h] = ht[((size_t)h << atot[j]) - 1];
+                }
+            p->last_derive = true;
+            p->desc += "[derived twiddles]";
         }
         if (d->kind == FFTB200_R2C) {
             const bool fused_r2c = p->passes.size() == 1 && p->passes[0].fused_lm && !getenv("FFTB200_NO_FUSED_R2C") &&

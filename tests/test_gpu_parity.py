@@ -120,6 +120,9 @@ def test_bluestein_fused_chirp_is_bit_identical(gpu, port, direction, monkeypatc
     in the same order: the outputs must be identical bit for bit (batch 3: ragged against the tile grid)."""
     n, b = 1000003, 3
     x = port.fill(52, 0, n * b).reshape(b, n)
+    # (without the factors riding on it the last pass of the plain transforms would run in the ring kernel, whose derived twiddles differ
+    # from the tile kernel's table twiddles in the last bits: keep both runs on the tile kernel, the comparison is about the factors)
+    monkeypatch.setenv("FFTB200_NO_LASTPIPE", "1")
     fused = gpu.gpu_fft_batch(x, direction)
     monkeypatch.setenv("FFTB200_NO_FUSED_CHIRP", "1")
     plain = gpu.gpu_fft_batch(x, direction)
@@ -390,20 +393,28 @@ def test_small_host_transforms_zero_copy_equals_staged(gpu, port, O, n, monkeypa
 @pytest.mark.parametrize("log_n,batch", [(22, 11), (23, 9), (24, 8)])
 @pytest.mark.parametrize("direction", [-1, 1])
 def test_tma_ring_last_pass_equals_tile_last_pass(gpu, port, O, log_n, batch, direction, monkeypatch):
-    """N = 2^22 .. 2^24, 8 or more transforms per execution: the last pass runs in fft_lastpipe_kernel (TMA ring, the fused
-    kernel's pass-B dataflow);
-    FFTB200_NO_LASTPIPE=1 keeps fft_tile_kernel<LAST>. Same table twiddles and butterflies: bit-identical where the radix
-    split is the same (2^23, 2^24), within 1e-15 otherwise; last transform against the oracle."""
+    """N = 2^22 .. 2^24: the last pass runs in fft_lastpipe_kernel (TMA ring, the fused kernel's pass-B dataflow); FFTB200_NO_LASTPIPE=1
+    keeps fft_tile_kernel<LAST>. With FFTB200_LASTPIPE_TABLE=1 the ring kernel loads every twiddle from the table like the tile kernel:
+    bit-identical where the radix split is the same (2^23, 2^24), within 1e-15 otherwise. By default it loads 4 of the 15 twiddles of a
+    radix-16 butterfly and derives the others as products with the table's own entries at kappa = 0 (the reference's recurrence is
+    multiplicative up to rounding noise - the noise is what differs: 2.9e-14 at 2^22, 7.5e-14 at 2^23, 2.9e-13 at 2^24, the largest size
+    that uses it); last transform against the oracle either way."""
     n = 1 << log_n
     x = port.fill(55, 0, n * batch).reshape(batch, n)
     y = gpu.gpu_fft_batch(x, direction)
     monkeypatch.setenv("FFTB200_NO_LASTPIPE", "1")
     z = gpu.gpu_fft_batch(x, direction)
     monkeypatch.delenv("FFTB200_NO_LASTPIPE")
+    monkeypatch.setenv("FFTB200_LASTPIPE_TABLE", "1")
+    w = gpu.gpu_fft_batch(x, direction)
+    monkeypatch.delenv("FFTB200_LASTPIPE_TABLE")
     if log_n >= 23:
-        assert np.array_equal(y, z)
+        assert np.array_equal(w, z)
     else:
-        assert O.rel_l2(y, z) <= 1e-15
+        assert O.rel_l2(w, z) <= 1e-15
+    d = O.rel_l2(y, z)
+    print("derived vs table twiddles, 2^%d: %.2e" % (log_n, d))
+    assert d <= (4e-13 if log_n == 24 else 1e-13)
     assert O.rel_l2(y[-1:], port.fft_batch(x[-1:], direction)) <= TOL
 
 
