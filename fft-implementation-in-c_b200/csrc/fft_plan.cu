@@ -1031,7 +1031,12 @@ extern "C" int fftb200_plan_create(fftb200_plan** out, const fftb200_plan_desc* 
                 cudaStreamSynchronize(cudaStreamLegacy) != cudaSuccess) { rc = fail("chirp upload failed"); break; }
             // b[k] = chirp[k], b[m-k] = chirp[k] (bluestein.c:116-121); FB = FFT_m(b), cached in the plan
             bluestein_wrap_kernel<<<(unsigned)((m + 255) / 256), 256, 0, p->stream>>>(p->fb, p->chirp, p->n, p->m);
-            rc = enqueue_c2c(p, p->fb, p->fb, 0, 1);
+            {   // (with every twiddle from the table: the spectrum of the chirp is computed once and multiplies every result)
+                const bool keep = p->last_derive;
+                p->last_derive = false;
+                rc = enqueue_c2c(p, p->fb, p->fb, 0, 1);
+                p->last_derive = keep;
+            }
             if (rc == 0 && cudaStreamSynchronize(p->stream) != cudaSuccess) rc = fail("Bluestein kernel spectrum failed: %s", cudaGetErrorString(cudaGetLastError()));
             if (rc != 0) break;
             p->launches = 2 * (int)p->passes.size() + (can_fuse_pre(p) ? 0 : 1) + (can_fuse_post(p) ? 0 : 2);
