@@ -40,13 +40,14 @@ __device__ __forceinline__ void table_twiddles(cd* tw, const cd* tp, const int a
 #pragma unroll
     for (int h = 1; h < (1 << R); h++) tw[h] = __ldg(tp + ((size_t)h << a_tot));
 }
-template <int R>
-__device__ __forceinline__ void last_twiddles(cd* tw, const cd* tp, const int a_tot, const int derive, const cd* d) {
-    if (derive) fused_twiddles<R>(tw, tp, a_tot, d);
+template <int R, bool DERIVE>
+__device__ __forceinline__ void last_twiddles(cd* tw, const cd* tp, const int a_tot, const cd* d) {
+    if constexpr (DERIVE) fused_twiddles<R>(tw, tp, a_tot, d);
     else table_twiddles<R>(tw, tp, a_tot);
 }
 
-template <int LR, bool INV>
+// DERIVE is compiled in (as a run-time switch next to the table loads it cost both forms 72 - 172 bytes of spills)
+template <int LR, bool INV, bool DERIVE>
 __global__ void __launch_bounds__(2 * PIPE_GROUP, 1) fft_lastpipe_kernel(const LastPipeArgs a) {
     static_assert(LR >= 5 && LR <= 9, "last pass of 32 .. 512 points");
     constexpr int LC2 = 12 - LR;                 // log2 k's per tile
@@ -145,7 +146,7 @@ __global__ void __launch_bounds__(2 * PIPE_GROUP, 1) fft_lastpipe_kernel(const L
 #pragma unroll
             for (int bb = 0; bb < NB; bb++) {
                 const G0 g(t + PIPE_GROUP * bb);
-                last_twiddles<RB0>(tw, a.tab + ((kb << LC2) + g.hi - 1), lm, a.derive, a.dtw[0]);
+                last_twiddles<RB0, DERIVE>(tw, a.tab + ((kb << LC2) + g.hi - 1), lm, a.dtw[0]);
                 SubStageGen<RB0, 1, 0, 0>::run(&x[bb * R0], tw);
             }
             group_sync(g2);   // every gather of sub-pass 0 is done (the layout changes)
@@ -162,7 +163,7 @@ __global__ void __launch_bounds__(2 * PIPE_GROUP, 1) fft_lastpipe_kernel(const L
             fused_gather<G1, SW1, 4, false>(x, sm, g1);
             {
                 cd tw[16];
-                last_twiddles<4>(tw, a.tab + ((kb << LC2) + g1.hi + ((size_t)g1.kloc << lm) - 1), lm + RB0, a.derive, a.dtw[1]);
+                last_twiddles<4, DERIVE>(tw, a.tab + ((kb << LC2) + g1.hi + ((size_t)g1.kloc << lm) - 1), lm + RB0, a.dtw[1]);
                 SubStageGen<4, 1, 0, 0>::run(x, tw);
             }
             group_sync(g2);
@@ -181,7 +182,7 @@ __global__ void __launch_bounds__(2 * PIPE_GROUP, 1) fft_lastpipe_kernel(const L
             // (asking for these 15 entries before the exchange settles - they only depend on the tile and the thread - spills
             // 190 bytes and is slower: 4.49 vs 4.21 ms at 2^24 x 16)
             cd tw[16];
-            last_twiddles<4>(tw, a.tab + ((kb << LC2) + gl.hi + ((size_t)gl.kloc << lm) - 1), lm + AL, a.derive, a.dtw[2]);
+            last_twiddles<4, DERIVE>(tw, a.tab + ((kb << LC2) + gl.hi + ((size_t)gl.kloc << lm) - 1), lm + AL, a.dtw[2]);
             SubStageGen<4, 1, 0, 0>::run(x, tw);
         }
         {
@@ -206,7 +207,7 @@ __global__ void __launch_bounds__(2 * PIPE_GROUP, 1) fft_lastpipe_kernel(const L
 }
 
 constexpr size_t LASTPIPE_SMEM = (size_t)PIPE_STAGES * PIPE_TILE * sizeof(cd) + 128;   // + barriers, tile numbers
-const void* lastpipe_func(int lr, int inverse);   // fft_kernels_lastpipe.cu
+const void* lastpipe_func(int lr, int inverse, int derive = 0);   // fft_kernels_lastpipe.cu
 cudaError_t launch_lastpipe(int lr, const LastPipeArgs& a, int grid, cudaStream_t s);
 
 }  // namespace fftb200

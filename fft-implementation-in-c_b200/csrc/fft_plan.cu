@@ -501,7 +501,8 @@ static int mark_lastpipe(fftb200_plan* p, DeviceState* ds) {
     // same-box A/B at 2^28 points (ms, ring / tile kernel): 2^21 4.03 / 4.04, 2^22 3.89 / 3.93, 2^23 3.96 / 4.30, 2^24 4.18 / 4.32, 2^25 4.82 / 4.61
     if (ps.log_p < 6 || ps.log_p > 8 || !lastpipe_func(ps.log_p, 0)) return 0;
     for (int iv = 0; iv < 2; iv++)
-        CU(cudaFuncSetAttribute(lastpipe_func(ps.log_p, iv), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LASTPIPE_SMEM));
+        for (int dv = 0; dv < 2; dv++)
+            CU(cudaFuncSetAttribute(lastpipe_func(ps.log_p, iv, dv), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LASTPIPE_SMEM));
     ps.lastpipe = ds->sms;
     p->desc += "[tma ring]";
     return 0;
